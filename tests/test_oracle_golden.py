@@ -176,7 +176,7 @@ def test_train_grads_and_adam():
         # Adam's first steps move every weight by ~lr*sign(g) regardless of |g|; where g ~ 0 the
         # sign is rounding noise, so a handful of weights may differ by up to 2*lr per step
         np.testing.assert_allclose(flat[::101], g[f"params_after_step{step}_sub"], atol=2.1e-3)
-        frac_exact = np.mean(np.abs(flat[::101] - g[f"params_after_step{step}_sub"]) < 2e-6)
+        frac_exact = np.mean(np.abs(flat[::101] - g[f"params_after_step{step}_sub"]) < 2e-5)
         assert frac_exact > 0.97, frac_exact
 
 
