@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the NeRF hot path (BASELINE.json metric: rays/s, 64 coarse + 128 importance samples).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render] [--impl ours|reference]
+
+Default workload = BASELINE.json configs[1]: one training step on a 1024-ray batch per GPU
+(render coarse+fine -> MSE -> backward -> Adam), bf16 tensor-core mode, synthetic rays, random-init
+8x256 NeRF.  N > 1 (launched by torchrun, one rank per GPU) is data-parallel with ONE flat gradient
+all-reduce per step (weak scaling: 1024 rays per GPU).  `--workload render` times BASELINE.json
+configs[2], the 800x800 (640k-ray) render sharded over the ranks (strong scaling).
+
+One JSON line on stdout (rank 0).  `value` = whole-job rays/s with inputs resident in HBM;
+`e2e` = the same step through the public API with rays/targets copied from pinned host memory and
+the loss read back every step; `roofline` = the fused MLP forward kernel (fine pass) against the
+measured bf16 tensor peak; `cpu_baseline` = the numpy oracle port timed on this box's host cores.
+`--impl reference` times that CPU path alone (the reference's own algorithm on the host cores).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_ROW_FWD = 1186816          # un-padded MACs x 2
+FLOP_PER_ROW_BWD = 2302208
+N_SAMPLES, N_IMPORTANCE = 64, 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", choices=["train", "render"], default="train")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (train) / total rays (render)")
+    ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on the host cores (bounded sample)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(workload, rays):
+    import numpy as np
+    from oracle import nerf_oracle as O
+    p = O.init_params(0)
+    o, d = O.random_rays(rays, 1)
+    tgt = np.random.default_rng(2).uniform(0, 1, (rays, 3)).astype(np.float32)
+    cfg = O.RenderConfig(N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
+    t_vals = np.linspace(0, 1, N_SAMPLES, dtype=np.float32)
+    u = np.linspace(0, 1, N_IMPORTANCE, dtype=np.float32)
+    rng = np.random.default_rng(3)
+    state = {"flat": O.flatten_params(p), "m": None, "v": None, "step": 0}
+
+    def train():
+        t_rand = rng.uniform(0, 1, (rays, N_SAMPLES)).astype(np.float32)
+        u_r = rng.uniform(0, 1, (rays, N_IMPORTANCE)).astype(np.float32)
+        prm = O.unflatten_params(state["flat"])
+        _, grads, _ = O.train_grads(prm, o, d, tgt, cfg, t_vals, u_r, t_rand)
+        if state["m"] is None:
+            state["m"] = np.zeros_like(state["flat"]); state["v"] = np.zeros_like(state["flat"])
+        state["step"] += 1
+        state["flat"], state["m"], state["v"] = O.adam_step(state["flat"], O.flatten_params(grads), state["m"],
+                                                            state["v"], state["step"])
+
+    def render():
+        O.render_rays(p, o, d, cfg, t_vals, u)
+
+    return train if workload == "train" else render
+
+
+def time_cpu(workload, rays, steps, warmup):
+    fn = cpu_step_fn(workload, rays)
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return statistics.median(ts)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's algorithm on the host cores (numpy oracle port; the
+    reference itself is pure Python/PyTorch and does not exist on the GPU box), same metric/config,
+    each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rays = 256 if args.workload == "train" else 512
+    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    sec = time_cpu(args.workload, rays, steps, warmup)
+    val = rays / sec
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": f"{args.workload}_rays_per_s", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, rays_override=rays),
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
+                             "sample": f"{rays}-ray {args.workload} step, 64+128 samples, numpy/OpenBLAS fp32, median of {steps}"},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, rays_override=None):
+    if args.workload == "train":
+        rays = rays_override or args.rays or 1024
+        return {"workload": f"train step: {rays}-ray batch per GPU, {N_SAMPLES}+{N_IMPORTANCE} samples, "
+                            "render+MSE+backward+Adam (BASELINE.json configs[1]; DP all-reduce for N>1)",
+                "rays_per_gpu": rays, "N_samples": N_SAMPLES, "N_importance": N_IMPORTANCE, "perturb": 1.0,
+                "parallelism": f"dp{args.gpus}",
+                "l2": "per-step working set (~1 GB of saved activations) exceeds the 126 MB L2; a 256 MB buffer is also rewritten between timed steps (untimed)"}
+    rays = rays_override or args.rays or 640000
+    return {"workload": f"render {rays} rays (800x800), {N_SAMPLES}+{N_IMPORTANCE} samples, chunk 16384, rays sharded over ranks "
+                        "(BASELINE.json configs[2])",
+            "rays_total": rays, "N_samples": N_SAMPLES, "N_importance": N_IMPORTANCE, "perturb": 0.0,
+            "parallelism": f"rays/{args.gpus}",
+            "l2": "640k rays x 256 samples stream >10 GB of intermediates per frame; a 256 MB buffer is also rewritten between timed steps (untimed)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as td
+    import nerf_mlp_b200 as nb
+    from nerf_mlp_b200 import ops
+    from oracle import nerf_oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    model = nb.NeRFMLP(precision=args.precision).to(dev)       # random-init 8x256 (torch default init)
+    if world > 1:
+        nb.dist.broadcast_params(model)
+    dll = nb._lib.dll()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    K, W = args.steps, max(args.warmup, 3)
+
+    # --- per-kernel timing hook: CUDA events around the fused MLP forward launches -----------------
+    mlp_events = []
+    orig_fwd = ops.mlp_fwd_rays
+
+    def timed_fwd(model_, rays_o, rays_d, z_vals, *a, **k):
+        if not timed_fwd.on:
+            return orig_fwd(model_, rays_o, rays_d, z_vals, *a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_fwd(model_, rays_o, rays_d, z_vals, *a, **k)
+        e1.record()
+        mlp_events.append((z_vals.numel(), e0, e1))
+        return out
+
+    timed_fwd.on = False
+    ops.mlp_fwd_rays = timed_fwd
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "train":
+        rays = args.rays or 1024
+        o_np, d_np = O.random_rays(rays, 100 + rank)
+        tgt_np = np.random.default_rng(200 + rank).uniform(0, 1, (rays, 3)).astype(np.float32)
+        o, d, tgt = (torch.from_numpy(a).to(dev) for a in (o_np, d_np, tgt_np))
+        renderer = nb.NeRFRenderer(model, dev, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=1.0)
+        opt = nb.FlatAdam(model, lr=5e-4)
+
+        def step(o_, d_, tgt_):
+            out = renderer._render_rays(o_, d_)
+            loss = ops.mse_loss(out["rgb_map"], tgt_)               # scripts/train.py:376
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+
+        units_per_step = rays * world
+        flop_per_unit = (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) * FLOP_PER_ROW_FWD + (N_SAMPLES + N_IMPORTANCE) * FLOP_PER_ROW_BWD
+        run = lambda: step(o, d, tgt)
+        ho, hd, ht = (torch.from_numpy(a).pin_memory() for a in (o_np, d_np, tgt_np))
+
+        def run_e2e():
+            o_ = ho.to(dev, non_blocking=True); d_ = hd.to(dev, non_blocking=True); t_ = ht.to(dev, non_blocking=True)
+            return float(step(o_, d_, t_))                          # loss read back: D2H + sync every step
+        h2d, d2h = 3 * rays * 12, 4
+    else:
+        total = args.rays or 640000
+        Himg = int(round(total ** 0.5))
+        if Himg * Himg != total:
+            Himg, Wimg = total, 1
+        else:
+            Wimg = Himg
+        o_np, d_np, focal = O.pinhole_rays(Himg, Wimg) if Wimg > 1 else (*O.random_rays(total, 1), 1.0)
+        lo, hi = nb.dist.shard_range(total, rank, world)
+        o, d = torch.from_numpy(o_np[lo:hi]).to(dev), torch.from_numpy(d_np[lo:hi]).to(dev)
+        renderer = nb.NeRFRenderer(model, dev, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=0.0)
+        n_local = hi - lo
+
+        def run():
+            return renderer.render(o, d, n_local, 1, focal)          # chunk loop of renderer.py:40-44 on this rank's block
+
+        ho, hd = torch.from_numpy(o_np[lo:hi]).pin_memory(), torch.from_numpy(d_np[lo:hi]).pin_memory()
+        hout = torch.empty((n_local, 1, 3), dtype=torch.float32).pin_memory()
+
+        def run_e2e():
+            img = renderer.render(ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True), n_local, 1, focal)
+            hout.copy_(img, non_blocking=True)
+            torch.cuda.synchronize()
+            return hout
+        units_per_step = total
+        flop_per_unit = (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) * FLOP_PER_ROW_FWD
+        h2d, d2h = 2 * n_local * 12, n_local * 12
+
+    # --- warm-up, then EXACTLY K timed steps (device time, per-step events, L2 flushed in between) ---
+    for _ in range(W):
+        run()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = dll.nerf_launch_count()
+    timed_fwd.on = True
+    evs = []
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(K):
+        flush.zero_()                                                # L2 flush, outside the event pair
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    timed_fwd.on = False
+    launches = dll.nerf_launch_count() - launches0
+    clocks = sampler.stop()
+    ms_steps = [a.elapsed_time(b) for a, b in evs]
+    ms_total = torch.tensor([sum(ms_steps)], device=dev, dtype=torch.float64)
+    if world > 1:
+        td.all_reduce(ms_total, op=td.ReduceOp.MAX)                 # max over ranks
+    ms_per_step = float(ms_total) / K
+    value = units_per_step / (ms_per_step * 1e-3)
+
+    # --- e2e: public API with host buffers, H2D + D2H inside the timed region (wall clock) ----------
+    for _ in range(2):
+        run_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        run_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        td.all_reduce(e2e_s, op=td.ReduceOp.MAX)
+    e2e_val = units_per_step * K / float(e2e_s)
+
+    # --- roofline of the dominant kernel: fused MLP forward (largest launch = fine pass) --------------
+    pk = peaks()
+    rows_max = max(n for n, _, _ in mlp_events)
+    fine = [(n, a.elapsed_time(b)) for n, a, b in mlp_events if n == rows_max]
+    avg_ms = sum(ms for _, ms in fine) / len(fine)
+    achieved = rows_max * FLOP_PER_ROW_FWD / (avg_ms * 1e-3) / 1e12
+    mlp_ms_per_step = sum(a.elapsed_time(b) for _, a, b in mlp_events) / K
+    roofline = {"kernel": "mlp_fwd_tc_kernel (fused PE + 8x256 MLP + heads), fine pass" if args.precision == "bf16" else "fp32 check-mode SGEMM chain",
+                "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + ", burst bf16 matmul",
+                "frac_of_sustained": (achieved / pk["bf16_tflops_sustained"]) if pk.get("bf16_tflops_sustained") else None,
+                "rows_per_launch": rows_max, "flop_per_row": FLOP_PER_ROW_FWD, "avg_launch_ms": avg_ms,
+                "mlp_fwd_share_of_step": mlp_ms_per_step / (sum(ms_steps) / K), "traffic": None}
+
+    line = {"metric": f"{args.workload}_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload == "train" else "strong",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args),
+            "step_tflops": units_per_step * flop_per_unit / (ms_per_step * 1e-3) / 1e12 / world,
+            "wall_s_timed_region": wall, "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "roofline": roofline}
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        rays_cpu = 256 if args.workload == "train" else 512
+        sec = time_cpu(args.workload, rays_cpu, 3, 1)
+        line["cpu_baseline"] = {"value": rays_cpu / sec, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{rays_cpu}-ray {args.workload} step, 64+128 samples, numpy/OpenBLAS fp32 oracle port, median of 3"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

