@@ -12,7 +12,8 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnerf_b200.so")
+# NERF_B200_LIB selects another build of the same library (kernel-variant sweeps); never a fallback
+LIB_PATH = os.environ.get("NERF_B200_LIB") or os.path.join(_HERE, "csrc", "libnerf_b200.so")
 
 N_PARAMS = 595844
 PREC_BF16, PREC_FP32 = 0, 1

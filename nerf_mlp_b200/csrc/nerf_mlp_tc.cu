@@ -12,23 +12,26 @@
 //              rgb head (128->3) on CUDA cores from the un-rounded fp32 accumulators; the view-
 //              direction part of view_linear is a per-ray fp32 vector ("view bias") added here.
 //
-// Warp roles: warp 0 = weight producer (one lane), warp 1 = MMA issuer (one lane), warps 2-5 /
-// 6-9 = prologue + epilogue of tile A / tile B.  The two tiles share every weight slot (tile B
-// trails tile A by kSkew slots), which halves the L2->SMEM weight traffic, and their epilogues
-// overlap the other tile's MMAs.  TMEM: 2 x 256 fp32 columns (all 512).
+// Warp roles: warp 0 = weight producer (one lane), warps 1 / 2 = MMA issuers of tile A / tile B
+// (one lane each; a single issuing thread was measured to be the bottleneck), warps 3-6 / 7-10 =
+// prologue + epilogue of tile A / tile B.  The two tiles share every weight slot (a slot is freed
+// when both issuers have committed it), which halves the L2->SMEM weight traffic; tile B starts
+// kSkew slots behind tile A so that each tile's epilogue overlaps the other tile's MMAs.
+// TMEM: 2 x 256 fp32 columns (all 512).
 #include "nerf_common.cuh"
 #include "tc_ptx.cuh"
 #include <mutex>
+#include <stdlib.h>
 #include <vector>
 
 #ifndef NERF_TC_NK
-#define NERF_TC_NK 1          // K-steps (16 wide) per weight slot
+#define NERF_TC_NK 2          // K-steps (16 wide) per weight slot
 #endif
 #ifndef NERF_TC_RING
-#define NERF_TC_RING 7        // ring slots
+#define NERF_TC_RING 3        // ring slots
 #endif
 #ifndef NERF_TC_SKEW
-#define NERF_TC_SKEW 3        // slots by which tile B trails tile A
+#define NERF_TC_SKEW 1        // slots by which tile B's issuer starts behind tile A's
 #endif
 
 namespace nerf {
@@ -38,10 +41,11 @@ constexpr int kNK = NERF_TC_NK;
 constexpr int kRing = NERF_TC_RING;
 constexpr int kSkew = NERF_TC_SKEW;
 static_assert(kNK == 1 || kNK == 2, "slot = 1 or 2 K-steps");
-static_assert(kSkew + 1 < kRing, "ring must hold the skew plus at least one prefetch slot");
+static_assert(kSkew >= 1 && kSkew + 1 < kRing, "ring must hold the skew plus at least one prefetch slot");
 constexpr int kSlotBytes = 8192 * kNK;            // 256 rows x 32 B x NK
 constexpr int kTileM = 128;
-constexpr int kThreads = 320;                     // producer, mma, 2 x 4 compute warps
+constexpr int kThreads = 352;                     // producer, 2 mma issuers, 2 x 4 compute warps
+constexpr int kFirstComputeWarp = 3;
 constexpr int kNumGemms = 10;
 
 // ---- shared memory map (bytes) ------------------------------------------------------------------
@@ -55,18 +59,19 @@ constexpr int kOnesBytes = 4096;
 constexpr int kOffHead = kOffOnes + kOnesBytes;              // w_sigma[256] w_rgb[3][128] b_sigma b_rgb[3]
 constexpr int kHeadFloats = 256 + 384 + 4;
 constexpr int kOffBar = kOffHead + ((kHeadFloats * 4 + 127) / 128) * 128;
-constexpr int kNumBars = 2 * kRing + 4;
+constexpr int kNumBars = 2 * kRing + 5;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 
 // ---- weight-slot schedule --------------------------------------------------------------------
 enum AKind : uint8_t { A_X = 0, A_ACT = 1, A_ONES = 2 };
-struct Slot {            // consumed by the kernel
+struct Slot {            // consumed by the kernel: one 16-byte constant-bank load per slot
   uint32_t goff, bytes;
-  uint16_t a_k0;
-  uint8_t nk, sw, a_kind, n8, first, last, gemm, pad[3];
+  uint32_t a_add;        // (byte offset of the first K-step inside the A tile) >> 4
+  uint32_t flags;        // bits 0-1 a_kind | 2 nk==2 | 3 first | 4 last | 5 N==128
 };
+constexpr uint32_t kFlagNk2 = 4, kFlagFirst = 8, kFlagLast = 16, kFlagN128 = 32;
 struct PackSlot {        // consumed by the pack kernel
   uint32_t goff;
   int32_t w_off, ldw, kvalid, b_off, n, nk, sw, is_bias;
@@ -103,27 +108,28 @@ static const Schedule& schedule() {
         for (int k0 = 0; k0 < g.klen[p]; k0 += 16 * kNK) {
           const int nk = (g.klen[p] - k0) / 16 < kNK ? (g.klen[p] - k0) / 16 : kNK;
           Slot sl{};
-          sl.goff = goff; sl.nk = (uint8_t)nk; sl.sw = (nk == 2) ? 64 : 32;
+          sl.goff = goff;
           sl.bytes = (uint32_t)g.n * 32 * nk;
-          sl.a_k0 = (uint16_t)k0; sl.a_kind = (uint8_t)g.kind[p]; sl.n8 = (uint8_t)(g.n / 8); sl.gemm = (uint8_t)gi;
+          sl.a_add = (uint32_t)((k0 >> 6) * 16384 + ((k0 & 63) >> 4) * 32) >> 4;
+          sl.flags = (uint32_t)g.kind[p] | (nk == 2 ? kFlagNk2 : 0) | (g.n == 128 ? kFlagN128 : 0);
           PackSlot ps{};
           ps.goff = goff; ps.ldw = kIn[g.layer]; ps.w_off = (int32_t)w_off(g.layer) + g.col0[p] + k0;
-          ps.kvalid = g.kvalid[p] - k0; ps.n = g.n; ps.nk = nk; ps.sw = sl.sw; ps.is_bias = 0; ps.b_off = 0;
+          ps.kvalid = g.kvalid[p] - k0; ps.n = g.n; ps.nk = nk; ps.sw = (nk == 2) ? 64 : 32; ps.is_bias = 0; ps.b_off = 0;
           s.slots.push_back(sl); s.pack.push_back(ps);
           goff += kSlotBytes;          // fixed stride keeps every slot 8 KB aligned in the image
         }
       }
       if (g.bias) {
         Slot sl{};
-        sl.goff = goff; sl.nk = 1; sl.sw = 32; sl.bytes = (uint32_t)g.n * 32; sl.a_k0 = 0; sl.a_kind = A_ONES;
-        sl.n8 = (uint8_t)(g.n / 8); sl.gemm = (uint8_t)gi;
+        sl.goff = goff; sl.bytes = (uint32_t)g.n * 32; sl.a_add = 0;
+        sl.flags = (uint32_t)A_ONES | (g.n == 128 ? kFlagN128 : 0);
         PackSlot ps{};
         ps.goff = goff; ps.n = g.n; ps.nk = 1; ps.sw = 32; ps.is_bias = 1; ps.b_off = (int32_t)b_off(g.layer);
         s.slots.push_back(sl); s.pack.push_back(ps);
         goff += kSlotBytes;
       }
-      s.slots[first_idx].first = 1;
-      s.slots.back().last = 1;
+      s.slots[first_idx].flags |= kFlagFirst;
+      s.slots.back().flags |= kFlagLast;
     }
     s.bytes = goff;
   });
@@ -147,7 +153,20 @@ static int upload_schedule() {
   return 0;
 }
 
-size_t mlp_tc_packed_bytes() { return schedule().bytes; }
+// All CTAs walk the weight image in the same order at the same time; with a single image every SM
+// hits the same few L2 slices at once (measured: the copies, not the MMAs, paced the kernel).  The
+// image is therefore replicated and CTA b streams from replica b % copies (still L2-resident:
+// copies x 1.3 MB of 126 MB).
+static int num_copies() {
+  static int n = [] {
+    const char* e = getenv("NERF_TC_COPIES");
+    int v = e ? atoi(e) : 16;
+    return v < 1 ? 1 : (v > 148 ? 148 : v);
+  }();
+  return n;
+}
+
+size_t mlp_tc_packed_bytes() { return schedule().bytes * (size_t)num_copies(); }
 
 // ---- swizzled K-major element offsets (bytes) -----------------------------------------------------
 // 16-byte chunk index XOR row bits, as applied by TMA / UMMA for SWIZZLE_{32,64,128}B.
@@ -162,9 +181,10 @@ __host__ __device__ __forceinline__ uint32_t sw32_off(int row, int k) {    // ro
 }
 
 // ---- pack: flat fp32 parameters -> bf16 slot image --------------------------------------------------
-__global__ void pack_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed) {
+__global__ void pack_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed, size_t image_bytes) {
   const int si = blockIdx.y;
   if (si >= c_nslots) return;
+  packed += (size_t)blockIdx.z * image_bytes;
   const PackSlot ps = c_pack[si];
   const int kw = 16 * ps.nk;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ps.n * kw; e += gridDim.x * blockDim.x) {
@@ -186,8 +206,8 @@ __global__ void pack_kernel(const float* __restrict__ params, uint8_t* __restric
 int mlp_tc_pack(const float* params, void* packed, cudaStream_t st) {
   int rc = upload_schedule();
   if (rc) return rc;
-  dim3 grid(8, (unsigned)schedule().slots.size());
-  pack_kernel<<<grid, 256, 0, st>>>(params, (uint8_t*)packed);
+  dim3 grid(8, (unsigned)schedule().slots.size(), (unsigned)num_copies());
+  pack_kernel<<<grid, 256, 0, st>>>(params, (uint8_t*)packed, schedule().bytes);
   NERF_LAUNCH_CHECK("pack_kernel");
   return 0;
 }
@@ -228,7 +248,7 @@ struct FwdArgs {
   const float* rays_o; const float* rays_d; const float* z_vals; int S; float coord_scale;
   const float* x_enc;
   int64_t M;
-  const uint8_t* packed;
+  const uint8_t* packed; size_t image_bytes; int ncopies;
   const float* params;
   const float* vb; int vb_div;
   float* out;
@@ -293,24 +313,27 @@ __device__ __forceinline__ void prologue(const FwdArgs& a, int64_t row, int m, u
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform by construction
+  const int lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + kOffBar;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (kRing + s); };
   auto bar_act = [&](int t) { return bar0 + 8u * (2 * kRing + t); };       // activations of tile t ready (epilogue -> MMA)
   auto bar_acc = [&](int t) { return bar0 + 8u * (2 * kRing + 2 + t); };   // accumulator of tile t ready (MMA -> epilogue)
+  const uint32_t bar_skew = bar0 + 8u * (2 * kRing + 4);                   // one-shot: tile A's issuer is kSkew slots in
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* head = reinterpret_cast<float*>(smem + kOffHead);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kRing; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < kRing; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 2); }
     for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), 128); mbar_init(bar_acc(t), 1); }
+    mbar_init(bar_skew, 1);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(sbase + kOffTmemPtr, 512); tmem_relinquish(); }
-  if (warp >= 2) {
-    const int tid = threadIdx.x - 64;                 // 0..255
+  if (warp >= kFirstComputeWarp) {
+    const int tid = threadIdx.x - 32 * kFirstComputeWarp;   // 0..255
     // constant A operand of the bias K-step: columns 0,1 = 1, rest 0 (SW32 layout)
     if (tid < 128) {
       const uint32_t one2 = 0x3F803F80u;              // bf16 (1.0, 1.0)
@@ -334,61 +357,65 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs a
   if (warp == 0) {
     // ================= weight producer =================
     if (lane == 0) {
+      const uint8_t* image = a.packed + (size_t)(blockIdx.x % a.ncopies) * a.image_bytes;
       uint32_t g = 0;
       for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
         for (int i = 0; i < nslots; ++i, ++g) {
           const uint32_t s = g % kRing, ph = (g / kRing) & 1;
+          const uint2 rec = *reinterpret_cast<const uint2*>(&c_slots[i]);      // goff, bytes
           mbar_wait(bar_empty(s), ph ^ 1, 100 + (int)s);
-          const uint32_t bytes = c_slots[i].bytes;
-          mbar_expect_tx(bar_full(s), bytes);
-          bulk_g2s(sbase + kOffRing + s * kSlotBytes, a.packed + c_slots[i].goff, bytes, bar_full(s));
+          mbar_expect_tx(bar_full(s), rec.y);
+          bulk_g2s(sbase + kOffRing + s * kSlotBytes, image + rec.x, rec.y, bar_full(s));
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      uint32_t gbase = 0;
-      uint32_t act_ph[2] = {0, 0};
-      auto issue = [&](int t, int i, bool wait_full) {
-        const Slot sl = c_slots[i];
-        const uint32_t g = gbase + i, s = g % kRing, ph = (g / kRing) & 1;
-        if (wait_full) mbar_wait(bar_full(s), ph, 200 + (int)s);
-        if (sl.first) { mbar_wait(bar_act(t), act_ph[t], 300 + t); act_ph[t] ^= 1; }
-        tc_fence_after();
-        const uint32_t idesc = make_idesc_bf16(kTileM, sl.n8 * 8);
-        const uint32_t d_tmem = tmem_base + (uint32_t)t * 256;
-        const uint32_t b_addr = sbase + kOffRing + s * kSlotBytes;
-        for (int ks = 0; ks < sl.nk; ++ks) {
-          const int k = sl.a_k0 + 16 * ks;
-          uint64_t adesc;
-          if (sl.a_kind == A_ONES) {
-            adesc = make_smem_desc(sbase + kOffOnes, 256, kSwz32);
-          } else {
-            const uint32_t abase = (sl.a_kind == A_X) ? (sbase + kOffX + t * kXBytes) : (sbase + kOffAct + t * kActBytes);
-            adesc = make_smem_desc(abase + (k >> 6) * 16384 + ((k & 63) >> 4) * 32, 1024, kSwz128);
-          }
-          const uint64_t bdesc = (sl.sw == 64) ? make_smem_desc(b_addr + ks * 32, 512, kSwz64)
-                                               : make_smem_desc(b_addr, 256, kSwz32);
-          mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (sl.first && ks == 0) ? 0u : 1u);
-        }
-        if (sl.last) tc_commit(bar_acc(t));
-      };
+  } else if (warp < kFirstComputeWarp) {
+    // ================= MMA issuers: warp 1 -> tile A, warp 2 -> tile B =================
+    // The whole warp walks the schedule (uniform control flow); one elected lane issues.
+    {
+      const int t = warp - 1;
+      // descriptor words that never change: hi = SBO | version | layout, lo = (addr >> 4) | LBO
+      constexpr uint32_t kHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t kHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
+      constexpr uint32_t kHiSw32 = (256u >> 4) | (1u << 14) | (6u << 29);
+      const uint32_t a_lo_x = ((sbase + kOffX + t * kXBytes) >> 4) | (1u << 16);
+      const uint32_t a_lo_act = ((sbase + kOffAct + t * kActBytes) >> 4) | (1u << 16);
+      const uint32_t a_lo_ones = ((sbase + kOffOnes) >> 4) | (1u << 16);
+      const uint32_t b_lo0 = ((sbase + kOffRing) >> 4) | (1u << 16);
+      const uint32_t d_tmem = tmem_base + (uint32_t)t * 256;
+      constexpr uint32_t kIdesc256 = make_idesc_bf16(kTileM, 256), kIdesc128 = make_idesc_bf16(kTileM, 128);
+      uint32_t s = 0, ph = 0, act_ph = 0;
+      if (t == 1) mbar_wait(bar_skew, 0, 500);            // one-shot start offset behind tile A
       for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
-        for (int i = 0; i < nslots + kSkew; ++i) {
-          if (i < nslots) issue(0, i, true);
-          const int j = i - kSkew;
-          if (j >= 0) {
-            issue(1, j, false);
-            tc_commit(bar_empty((gbase + j) % kRing));     // slot is free once both tiles' MMAs retired
+        for (int i = 0; i < nslots; ++i) {
+          const uint4 rec = *reinterpret_cast<const uint4*>(&c_slots[i]);
+          const uint32_t a_add = rec.z, fl = rec.w;
+          mbar_wait(bar_full(s), ph, 200 + (int)s);
+          if (fl & kFlagFirst) { mbar_wait(bar_act(t), act_ph, 300 + t); act_ph ^= 1; }
+          tc_fence_after();
+          const uint32_t kind = fl & 3u;
+          const uint32_t a_lo = (kind == A_X ? a_lo_x : (kind == A_ACT ? a_lo_act : a_lo_ones)) + a_add;
+          const uint32_t a_hi = (kind == A_ONES) ? kHiSw32 : kHiSw128;
+          const uint32_t b_lo = b_lo0 + s * (kSlotBytes >> 4);
+          const uint32_t b_hi = (fl & kFlagNk2) ? kHiSw64 : kHiSw32;
+          const uint32_t idesc = (fl & kFlagN128) ? kIdesc128 : kIdesc256;
+          if (elect_one()) {
+            mma_bf16_ss(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
+                        (fl & kFlagFirst) ? 0u : 1u);
+            if (fl & kFlagNk2)
+              mma_bf16_ss(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2), ((uint64_t)b_hi << 32) | (b_lo + 2), idesc, 1u);
+            tc_commit(bar_empty(s));                      // slot is free once both issuers' MMAs on it retired
+            if (fl & kFlagLast) tc_commit(bar_acc(t));
+            if (t == 0 && i == kSkew - 1 && pair == (int)blockIdx.x) mbar_arrive(bar_skew);
           }
+          __syncwarp();
+          if (++s == kRing) { s = 0; ph ^= 1; }
         }
-        gbase += nslots;
       }
     }
   } else {
     // ================= prologue + epilogue warps =================
-    const int t = (warp - 2) >> 2;                    // tile A / tile B
+    const int t = (warp - kFirstComputeWarp) >> 2;    // tile A / tile B
     const int q = warp & 3;                           // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;                      // row within the tile
     uint8_t* xt = smem + kOffX + t * kXBytes;
@@ -520,6 +547,7 @@ int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals
   FwdArgs a{};
   a.rays_o = rays_o; a.rays_d = rays_d; a.z_vals = z_vals; a.S = S; a.coord_scale = coord_scale;
   a.x_enc = x_enc; a.M = M; a.packed = (const uint8_t*)packed; a.params = params;
+  a.image_bytes = schedule().bytes; a.ncopies = num_copies();
   a.vb = vb; a.vb_div = (x_enc != nullptr) ? 1 : S;
   a.out = out;
   a.save = save ? (__nv_bfloat16*)((uint8_t*)ws + (size_t)M * 128 * sizeof(float)) : nullptr;
