@@ -83,8 +83,10 @@ int nerf_mlp_fwd_encoded(const float* x_enc, const float* d_enc, int64_t M, cons
 
 /* Backward of either forward (the implicit autograd at scripts/train.py:382): given d_raw[M,4]
  * and the workspace written by a forward with save=1, ACCUMULATES into flat_grads[NERF_N_PARAMS]
- * (same layout as params).  Inputs receive no gradient. */
-int nerf_mlp_bwd(const float* d_raw, int64_t M, const float* params, const void* packed,
+ * (same layout as params).  Inputs receive no gradient.
+ * rows_per_dir = samples per ray S for nerf_mlp_fwd_rays (rows sharing one view direction),
+ * 1 for nerf_mlp_fwd_encoded. */
+int nerf_mlp_bwd(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
                  float* flat_grads, void* workspace, size_t workspace_bytes, int precision,
                  void* stream);
 

@@ -32,7 +32,7 @@ SIGNATURES = {
     "nerf_mlp_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "nerf_mlp_fwd_rays": (c_int, [_P, _P, _P, c_int, c_int, c_float, _P, _P, _P, _P, c_size_t, c_int, c_int, _P]),
     "nerf_mlp_fwd_encoded": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_size_t, c_int, c_int, _P]),
-    "nerf_mlp_bwd": (c_int, [_P, c_int64, _P, _P, _P, _P, c_size_t, c_int, _P]),
+    "nerf_mlp_bwd": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_size_t, c_int, _P]),
     "nerf_composite_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "nerf_composite_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "nerf_sample_pdf": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),

@@ -90,7 +90,7 @@ extern "C" int nerf_mlp_fwd_encoded(const float* x_enc, const float* d_enc, int6
                         workspace, workspace_bytes, save, (cudaStream_t)stream);
 }
 
-extern "C" int nerf_mlp_bwd(const float* d_raw, int64_t M, const float* params, const void* packed,
+extern "C" int nerf_mlp_bwd(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
                             float* flat_grads, void* workspace, size_t workspace_bytes, int precision,
                             void* stream) {
   NERF_CHECK_ARG(M >= 0, "nerf_mlp_bwd: bad M=%lld", (long long)M);
@@ -99,5 +99,5 @@ extern "C" int nerf_mlp_bwd(const float* d_raw, int64_t M, const float* params, 
   NERF_CHECK_ARG(d_raw && params && flat_grads && workspace, "nerf_mlp_bwd: null pointer");
   if (precision == NERF_PREC_FP32)
     return mlp_fp32_backward(d_raw, M, params, flat_grads, (float*)workspace, workspace_bytes, (cudaStream_t)stream);
-  return mlp_tc_backward(d_raw, M, params, packed, flat_grads, workspace, workspace_bytes, (cudaStream_t)stream);
+  return mlp_tc_backward(d_raw, M, rows_per_dir, params, packed, flat_grads, workspace, workspace_bytes, (cudaStream_t)stream);
 }

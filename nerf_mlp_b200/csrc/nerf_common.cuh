@@ -80,7 +80,7 @@ int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals
                    float coord_scale, const float* x_enc, const float* d_enc, int64_t M,
                    const float* params, const void* packed, float* out, void* ws, size_t ws_bytes,
                    int save, cudaStream_t st);
-int mlp_tc_backward(const float* d_raw, int64_t M, const float* params, const void* packed,
+int mlp_tc_backward(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
                     float* grads, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace nerf

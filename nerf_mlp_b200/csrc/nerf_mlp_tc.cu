@@ -1,4 +1,5 @@
-// Fused NeRF MLP forward on the 5th-gen tensor cores (tcgen05, sm_100a).
+// Fused NeRF MLP on the 5th-gen tensor cores (tcgen05, sm_100a): forward and the dgrad chain of
+// the backward.  (The weight gradients are in nerf_mlp_wgrad.cu.)
 //
 // One persistent CTA per SM processes PAIRS of 128-row sample tiles.  Per tile the whole network
 // (reference model.py:57-81) runs on-chip:
@@ -12,41 +13,26 @@
 //              rgb head (128->3) on CUDA cores from the un-rounded fp32 accumulators; the view-
 //              direction part of view_linear is a per-ray fp32 vector ("view bias") added here.
 //
+// The backward dgrad chain (d_raw -> d(pre-activation) of every layer) is the same machine run
+// over the transposed weight image: 9 GEMMs per tile, epilogue = ReLU mask (bit masks saved by the
+// forward) -> bf16 -> SMEM + HBM (operands of the wgrad kernel).
+//
 // Warp roles: warp 0 = weight producer (one lane), warps 1 / 2 = MMA issuers of tile A / tile B
 // (one lane each; a single issuing thread was measured to be the bottleneck), warps 3-6 / 7-10 =
 // prologue + epilogue of tile A / tile B.  The two tiles share every weight slot (a slot is freed
 // when both issuers have committed it), which halves the L2->SMEM weight traffic; tile B starts
 // kSkew slots behind tile A so that each tile's epilogue overlaps the other tile's MMAs.
 // TMEM: 2 x 256 fp32 columns (all 512).
-#include "nerf_common.cuh"
-#include "tc_ptx.cuh"
+#include "tc_common.cuh"
 #include <mutex>
-#include <stdlib.h>
 #include <vector>
-
-#ifndef NERF_TC_NK
-#define NERF_TC_NK 2          // K-steps (16 wide) per weight slot
-#endif
-#ifndef NERF_TC_RING
-#define NERF_TC_RING 3        // ring slots
-#endif
-#ifndef NERF_TC_SKEW
-#define NERF_TC_SKEW 1        // slots by which tile B's issuer starts behind tile A's
-#endif
 
 namespace nerf {
 using namespace ptx;
 
-constexpr int kNK = NERF_TC_NK;
-constexpr int kRing = NERF_TC_RING;
-constexpr int kSkew = NERF_TC_SKEW;
-static_assert(kNK == 1 || kNK == 2, "slot = 1 or 2 K-steps");
-static_assert(kSkew >= 1 && kSkew + 1 < kRing, "ring must hold the skew plus at least one prefetch slot");
-constexpr int kSlotBytes = 8192 * kNK;            // 256 rows x 32 B x NK
-constexpr int kTileM = 128;
 constexpr int kThreads = 352;                     // producer, 2 mma issuers, 2 x 4 compute warps
 constexpr int kFirstComputeWarp = 3;
-constexpr int kNumGemms = 10;
+constexpr int kNumGemmsFwd = 10, kNumGemmsBwd = 9;
 
 // ---- shared memory map (bytes) ------------------------------------------------------------------
 constexpr int kOffAct = 0;                                   // 2 x [128 x 256] bf16, SW128 K-blocks of 64
@@ -64,26 +50,14 @@ constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 
-// ---- weight-slot schedule --------------------------------------------------------------------
-enum AKind : uint8_t { A_X = 0, A_ACT = 1, A_ONES = 2 };
-struct Slot {            // consumed by the kernel: one 16-byte constant-bank load per slot
-  uint32_t goff, bytes;
-  uint32_t a_add;        // (byte offset of the first K-step inside the A tile) >> 4
-  uint32_t flags;        // bits 0-1 a_kind | 2 nk==2 | 3 first | 4 last | 5 N==128
-};
-constexpr uint32_t kFlagNk2 = 4, kFlagFirst = 8, kFlagLast = 16, kFlagN128 = 32;
-struct PackSlot {        // consumed by the pack kernel
-  uint32_t goff;
-  int32_t w_off, ldw, kvalid, b_off, n, nk, sw, is_bias;
-};
-constexpr int kMaxSlots = 192;
-__constant__ Slot c_slots[kMaxSlots];
+__constant__ Slot c_slots[kMaxSlots];          // forward schedule, then the dgrad schedule
 __constant__ PackSlot c_pack[kMaxSlots];
-__constant__ int c_nslots;
+__constant__ int c_nslots_fwd, c_nslots_bwd;
 
 struct Schedule {
   std::vector<Slot> slots;
   std::vector<PackSlot> pack;
+  int n_fwd = 0, n_bwd = 0;
   size_t bytes = 0;
 };
 
@@ -91,46 +65,61 @@ static const Schedule& schedule() {
   static Schedule s;
   static std::once_flag once;
   std::call_once(once, [] {
-    struct G { int layer, n, bias; int nparts; int kind[2], klen[2], col0[2], kvalid[2]; };
-    std::vector<G> gs;
-    gs.push_back({0, 256, 1, 1, {A_X, 0}, {64, 0}, {0, 0}, {63, 0}});
-    for (int l = 1; l <= 4; ++l) gs.push_back({l, 256, 1, 1, {A_ACT, 0}, {256, 0}, {0, 0}, {256, 0}});
-    gs.push_back({5, 256, 1, 2, {A_X, A_ACT}, {64, 256}, {0, 63}, {63, 256}});   // [x, h] concat (model.py:62-63)
-    gs.push_back({6, 256, 1, 1, {A_ACT, 0}, {256, 0}, {0, 0}, {256, 0}});
-    gs.push_back({7, 256, 1, 1, {A_ACT, 0}, {256, 0}, {0, 0}, {256, 0}});
-    gs.push_back({L_BOTT, 256, 1, 1, {A_ACT, 0}, {256, 0}, {0, 0}, {256, 0}});
-    gs.push_back({L_VIEW, 128, 0, 1, {A_ACT, 0}, {256, 0}, {0, 0}, {256, 0}});   // dirs part + bias live in the view bias
+    // One GEMM of a schedule: `parts` of the A operand (tile kind, K length), the weight block it
+    // multiplies (value(n,k) = params[w0 + n*ns + k*ks], k < kvalid), N, and an optional bias K-step.
+    struct Part { int kind, klen, w0, ns, ks, kvalid; };
+    struct G { int n, b_off; std::vector<Part> parts; };
+    std::vector<G> fwd, bwd;
+    auto W = [](int l) { return (int)w_off(l); };
+    // ---- forward (reference model.py:57-81)
+    fwd.push_back({256, (int)b_off(0), {{A_X, 64, W(0), 63, 1, 63}}});
+    for (int l = 1; l <= 4; ++l) fwd.push_back({256, (int)b_off(l), {{A_ACT, 256, W(l), 256, 1, 256}}});
+    fwd.push_back({256, (int)b_off(5), {{A_X, 64, W(5), 319, 1, 63}, {A_ACT, 256, W(5) + 63, 319, 1, 256}}});  // [x,h] :62-63
+    fwd.push_back({256, (int)b_off(6), {{A_ACT, 256, W(6), 256, 1, 256}}});
+    fwd.push_back({256, (int)b_off(7), {{A_ACT, 256, W(7), 256, 1, 256}}});
+    fwd.push_back({256, (int)b_off(L_BOTT), {{A_ACT, 256, W(L_BOTT), 256, 1, 256}}});
+    fwd.push_back({128, -1, {{A_ACT, 256, W(L_VIEW), 283, 1, 256}}});     // dirs part + bias live in the view bias
+    // ---- dgrad chain: dX = dY . W, i.e. B(n = in-feature, k = out-feature) = W[k][n]
+    bwd.push_back({256, -1, {{A_ACT, 128, W(L_VIEW), 1, 283, 128}}});     // d_bott   = d_hv_pre . W_view[:, :256]
+    bwd.push_back({256, -1, {{A_ACT, 256, W(L_BOTT), 1, 256, 256}}});     // d_h7     = d_bott . W_bott (+ sigma term)
+    for (int l = 7; l >= 1; --l)                                          // d_h{l-1} = d_pre_l . W_l[:, h part]
+      bwd.push_back({256, -1, {{A_ACT, 256, W(l) + (l == 5 ? 63 : 0), 1, kIn[l], 256}}});
     uint32_t goff = 0;
-    for (size_t gi = 0; gi < gs.size(); ++gi) {
-      const G& g = gs[gi];
-      const size_t first_idx = s.slots.size();
-      for (int p = 0; p < g.nparts; ++p) {
-        for (int k0 = 0; k0 < g.klen[p]; k0 += 16 * kNK) {
-          const int nk = (g.klen[p] - k0) / 16 < kNK ? (g.klen[p] - k0) / 16 : kNK;
-          Slot sl{};
-          sl.goff = goff;
-          sl.bytes = (uint32_t)g.n * 32 * nk;
-          sl.a_add = (uint32_t)((k0 >> 6) * 16384 + ((k0 & 63) >> 4) * 32) >> 4;
-          sl.flags = (uint32_t)g.kind[p] | (nk == 2 ? kFlagNk2 : 0) | (g.n == 128 ? kFlagN128 : 0);
-          PackSlot ps{};
-          ps.goff = goff; ps.ldw = kIn[g.layer]; ps.w_off = (int32_t)w_off(g.layer) + g.col0[p] + k0;
-          ps.kvalid = g.kvalid[p] - k0; ps.n = g.n; ps.nk = nk; ps.sw = (nk == 2) ? 64 : 32; ps.is_bias = 0; ps.b_off = 0;
-          s.slots.push_back(sl); s.pack.push_back(ps);
-          goff += kSlotBytes;          // fixed stride keeps every slot 8 KB aligned in the image
+    auto emit = [&](const std::vector<G>& gs) {
+      for (const G& g : gs) {
+        const size_t first_idx = s.slots.size();
+        for (const Part& p : g.parts) {
+          for (int k0 = 0; k0 < p.klen; k0 += 16 * kNK) {
+            const int nk = (p.klen - k0) / 16 < kNK ? (p.klen - k0) / 16 : kNK;
+            Slot sl{};
+            sl.goff = goff;
+            sl.bytes = (uint32_t)g.n * 32 * nk;
+            sl.a_add = (uint32_t)((k0 >> 6) * 16384 + ((k0 & 63) >> 4) * 32) >> 4;
+            sl.flags = (uint32_t)p.kind | (nk == 2 ? kFlagNk2 : 0) | (g.n == 128 ? kFlagN128 : 0);
+            PackSlot ps{};
+            ps.goff = goff; ps.w_base = p.w0 + k0 * p.ks; ps.n_stride = p.ns; ps.k_stride = p.ks;
+            ps.kvalid = p.kvalid - k0; ps.n = g.n; ps.nk = nk; ps.sw = (nk == 2) ? 64 : 32;
+            s.slots.push_back(sl); s.pack.push_back(ps);
+            goff += kSlotBytes;          // fixed stride keeps every slot 8 KB aligned in the image
+          }
         }
+        if (g.b_off >= 0) {
+          Slot sl{};
+          sl.goff = goff; sl.bytes = (uint32_t)g.n * 32; sl.a_add = 0;
+          sl.flags = (uint32_t)A_ONES | (g.n == 128 ? kFlagN128 : 0);
+          PackSlot ps{};
+          ps.goff = goff; ps.n = g.n; ps.nk = 1; ps.sw = 32; ps.is_bias = 1; ps.b_off = g.b_off;
+          s.slots.push_back(sl); s.pack.push_back(ps);
+          goff += kSlotBytes;
+        }
+        s.slots[first_idx].flags |= kFlagFirst;
+        s.slots.back().flags |= kFlagLast;
       }
-      if (g.bias) {
-        Slot sl{};
-        sl.goff = goff; sl.bytes = (uint32_t)g.n * 32; sl.a_add = 0;
-        sl.flags = (uint32_t)A_ONES | (g.n == 128 ? kFlagN128 : 0);
-        PackSlot ps{};
-        ps.goff = goff; ps.n = g.n; ps.nk = 1; ps.sw = 32; ps.is_bias = 1; ps.b_off = (int32_t)b_off(g.layer);
-        s.slots.push_back(sl); s.pack.push_back(ps);
-        goff += kSlotBytes;
-      }
-      s.slots[first_idx].flags |= kFlagFirst;
-      s.slots.back().flags |= kFlagLast;
-    }
+    };
+    emit(fwd);
+    s.n_fwd = (int)s.slots.size();
+    emit(bwd);
+    s.n_bwd = (int)s.slots.size() - s.n_fwd;
     s.bytes = goff;
   });
   return s;
@@ -148,43 +137,18 @@ static int upload_schedule() {
   NERF_CHECK_ARG(n <= kMaxSlots, "slot table overflow (%d)", n);
   NERF_CUDA(cudaMemcpyToSymbol(c_slots, s.slots.data(), n * sizeof(Slot)));
   NERF_CUDA(cudaMemcpyToSymbol(c_pack, s.pack.data(), n * sizeof(PackSlot)));
-  NERF_CUDA(cudaMemcpyToSymbol(c_nslots, &n, sizeof(int)));
+  NERF_CUDA(cudaMemcpyToSymbol(c_nslots_fwd, &s.n_fwd, sizeof(int)));
+  NERF_CUDA(cudaMemcpyToSymbol(c_nslots_bwd, &s.n_bwd, sizeof(int)));
   if (dev < 64) done[dev] = true;
   return 0;
 }
 
-// All CTAs walk the weight image in the same order at the same time; with a single image every SM
-// hits the same few L2 slices at once (measured: the copies, not the MMAs, paced the kernel).  The
-// image is therefore replicated and CTA b streams from replica b % copies (still L2-resident:
-// copies x 1.3 MB of 126 MB).
-static int num_copies() {
-  static int n = [] {
-    const char* e = getenv("NERF_TC_COPIES");
-    int v = e ? atoi(e) : 16;
-    return v < 1 ? 1 : (v > 148 ? 148 : v);
-  }();
-  return n;
-}
+size_t mlp_tc_packed_bytes() { return schedule().bytes; }
 
-size_t mlp_tc_packed_bytes() { return schedule().bytes * (size_t)num_copies(); }
-
-// ---- swizzled K-major element offsets (bytes) -----------------------------------------------------
-// 16-byte chunk index XOR row bits, as applied by TMA / UMMA for SWIZZLE_{32,64,128}B.
-__host__ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {   // rows of 128 B (64 bf16)
-  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ row) & 7) << 4) + (k & 7) * 2);
-}
-__host__ __device__ __forceinline__ uint32_t sw64_off(int row, int k) {    // rows of 64 B (32 bf16)
-  return (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((((k >> 3) ^ (row >> 1)) & 3) << 4) + (k & 7) * 2);
-}
-__host__ __device__ __forceinline__ uint32_t sw32_off(int row, int k) {    // rows of 32 B (16 bf16)
-  return (uint32_t)((row >> 3) * 256 + (row & 7) * 32 + ((((k >> 3) ^ (row >> 2)) & 1) << 4) + (k & 7) * 2);
-}
-
-// ---- pack: flat fp32 parameters -> bf16 slot image --------------------------------------------------
-__global__ void pack_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed, size_t image_bytes) {
+// ---- pack: flat fp32 parameters -> bf16 slot images (forward + transposed) ----------------------
+__global__ void pack_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed, int nslots) {
   const int si = blockIdx.y;
-  if (si >= c_nslots) return;
-  packed += (size_t)blockIdx.z * image_bytes;
+  if (si >= nslots) return;
   const PackSlot ps = c_pack[si];
   const int kw = 16 * ps.nk;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ps.n * kw; e += gridDim.x * blockDim.x) {
@@ -196,7 +160,7 @@ __global__ void pack_kernel(const float* __restrict__ params, uint8_t* __restric
       if (kk == 0) v = hi;
       else if (kk == 1) v = b - hi;          // lo part: bias reaches the accumulator with ~16 mantissa bits
     } else if (kk < ps.kvalid) {
-      v = params[ps.w_off + (int64_t)n * ps.ldw + kk];
+      v = params[ps.w_base + (int64_t)n * ps.n_stride + (int64_t)kk * ps.k_stride];
     }
     const uint32_t off = (ps.sw == 64) ? sw64_off(n, kk) : sw32_off(n, kk);
     *reinterpret_cast<__nv_bfloat16*>(packed + ps.goff + off) = __float2bfloat16_rn(v);
@@ -206,8 +170,9 @@ __global__ void pack_kernel(const float* __restrict__ params, uint8_t* __restric
 int mlp_tc_pack(const float* params, void* packed, cudaStream_t st) {
   int rc = upload_schedule();
   if (rc) return rc;
-  dim3 grid(8, (unsigned)schedule().slots.size(), (unsigned)num_copies());
-  pack_kernel<<<grid, 256, 0, st>>>(params, (uint8_t*)packed, schedule().bytes);
+  const int n = (int)schedule().slots.size();
+  dim3 grid(8, (unsigned)n);
+  pack_kernel<<<grid, 256, 0, st>>>(params, (uint8_t*)packed, n);
   NERF_LAUNCH_CHECK("pack_kernel");
   return 0;
 }
@@ -217,7 +182,7 @@ int mlp_tc_pack(const float* params, void* packed, cudaStream_t st) {
 // (reference renderer.py:72-74); encoded entry: one row per sample from d_enc.
 __global__ void __launch_bounds__(128) view_bias_kernel(const float* __restrict__ rays_d, const float* __restrict__ d_enc,
                                                        int64_t nrows, const float* __restrict__ params,
-                                                       float* __restrict__ vb) {
+                                                       float* __restrict__ vb, float* __restrict__ de_out) {
   __shared__ float de[27];
   const int64_t row = blockIdx.x;
   if (threadIdx.x < 27 && d_enc != nullptr) de[threadIdx.x] = d_enc[row * 27 + threadIdx.x];
@@ -241,23 +206,31 @@ __global__ void __launch_bounds__(128) view_bias_kernel(const float* __restrict_
 #pragma unroll
   for (int j = 0; j < 27; ++j) acc = fmaf(w[j], de[j], acc);
   vb[row * 128 + n] = acc;
+  if (de_out != nullptr && n < 32) de_out[row * 32 + n] = n < 27 ? de[n] : 0.f;
 }
 
-// ---- the fused forward kernel -------------------------------------------------------------------
-struct FwdArgs {
+// ---- kernel arguments ---------------------------------------------------------------------------------
+struct TcArgs {
+  // forward inputs
   const float* rays_o; const float* rays_d; const float* z_vals; int S; float coord_scale;
   const float* x_enc;
-  int64_t M;
-  const uint8_t* packed; size_t image_bytes; int ncopies;
-  const float* params;
   const float* vb; int vb_div;
-  float* out;
-  __nv_bfloat16* save;
+  float* out;                       // [M,4]
+  // backward input
+  const float* d_raw;               // [M,4]
+  // common
+  int64_t M;
+  const uint8_t* packed;
+  const float* params;
+  // saved tensors (forward writes when kSave, dgrad reads)
+  __nv_bfloat16* act; __nv_bfloat16* hv; __nv_bfloat16* xenc; uint32_t* mask; uint32_t* hvmask;
+  // dgrad outputs
+  __nv_bfloat16* dpre; __nv_bfloat16* dhv;
   int num_pairs;
 };
 
 // bf16 x-tile row: 63 encoded channels (+ a zero pad column) -> 8 swizzled 16-byte chunks
-__device__ __forceinline__ void store_x_row(uint8_t* xt, int m, const float (&v)[64]) {
+__device__ __forceinline__ void store_x_row(uint8_t* xt, int m, const float (&v)[64], __nv_bfloat16* save_row) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     uint4 q;
@@ -266,10 +239,11 @@ __device__ __forceinline__ void store_x_row(uint8_t* xt, int m, const float (&v)
     q.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
     q.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
     *reinterpret_cast<uint4*>(xt + sw128_off(m, 8 * c)) = q;
+    if (save_row != nullptr) *reinterpret_cast<uint4*>(save_row + 8 * c) = q;
   }
 }
 
-__device__ __forceinline__ void prologue(const FwdArgs& a, int64_t row, int m, uint8_t* xt) {
+__device__ __forceinline__ void fwd_prologue(const TcArgs& a, int64_t row, int m, uint8_t* xt, bool save) {
   float v[64];
 #pragma unroll
   for (int j = 0; j < 64; ++j) v[j] = 0.f;
@@ -308,10 +282,19 @@ __device__ __forceinline__ void prologue(const FwdArgs& a, int64_t row, int m, u
       }
     }
   }
-  store_x_row(xt, m, v);
+  store_x_row(xt, m, v, (save && row < a.M) ? a.xenc + row * 64 : nullptr);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs a) {
+__device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&r)[32]) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) w |= (__uint_as_float(r[j]) > 0.f) ? (1u << j) : 0u;
+  return w;
+}
+
+// kBwd = false: forward (kSave: also write the tensors the backward needs); kBwd = true: dgrad chain
+template <bool kBwd, bool kSave>
+__global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
@@ -324,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs a
   const uint32_t bar_skew = bar0 + 8u * (2 * kRing + 4);                   // one-shot: tile A's issuer is kSkew slots in
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* head = reinterpret_cast<float*>(smem + kOffHead);
+  constexpr int kNumGemms = kBwd ? kNumGemmsBwd : kNumGemmsFwd;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kRing; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 2); }
@@ -352,20 +336,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs a
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int nslots = c_nslots;
+  const int slot0 = kBwd ? c_nslots_fwd : 0;
+  const int nslots = kBwd ? c_nslots_bwd : c_nslots_fwd;
 
   if (warp == 0) {
     // ================= weight producer =================
     if (lane == 0) {
-      const uint8_t* image = a.packed + (size_t)(blockIdx.x % a.ncopies) * a.image_bytes;
       uint32_t g = 0;
       for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
         for (int i = 0; i < nslots; ++i, ++g) {
           const uint32_t s = g % kRing, ph = (g / kRing) & 1;
-          const uint2 rec = *reinterpret_cast<const uint2*>(&c_slots[i]);      // goff, bytes
+          const uint2 rec = *reinterpret_cast<const uint2*>(&c_slots[slot0 + i]);      // goff, bytes
           mbar_wait(bar_empty(s), ph ^ 1, 100 + (int)s);
           mbar_expect_tx(bar_full(s), rec.y);
-          bulk_g2s(sbase + kOffRing + s * kSlotBytes, image + rec.x, rec.y, bar_full(s));
+          bulk_g2s(sbase + kOffRing + s * kSlotBytes, a.packed + rec.x, rec.y, bar_full(s));
         }
       }
     }
@@ -388,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs a
       if (t == 1) mbar_wait(bar_skew, 0, 500);            // one-shot start offset behind tile A
       for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
         for (int i = 0; i < nslots; ++i) {
-          const uint4 rec = *reinterpret_cast<const uint4*>(&c_slots[i]);
+          const uint4 rec = *reinterpret_cast<const uint4*>(&c_slots[slot0 + i]);
           const uint32_t a_add = rec.z, fl = rec.w;
           mbar_wait(bar_full(s), ph, 200 + (int)s);
           if (fl & kFlagFirst) { mbar_wait(bar_act(t), act_ph, 300 + t); act_ph ^= 1; }
@@ -425,87 +409,165 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs a
     for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
       const int64_t row = ((int64_t)pair * 2 + t) * kTileM + m;
       const bool valid = row < a.M;
-      prologue(a, row, m, xt);
-      fence_proxy_async();
-      mbar_arrive(bar_act(t));
-      float sigma = head[640];
-      for (int g = 0; g < kNumGemms; ++g) {
-        mbar_wait(bar_acc(t), acc_ph, 400 + t);
-        acc_ph ^= 1;
-        tc_fence_after();
-        if (g < 9) {
-          __nv_bfloat16* sv = (a.save != nullptr && valid) ? a.save + ((int64_t)g * a.M + row) * 256 : nullptr;
+      if constexpr (!kBwd) {
+        // ------------------------------ forward ------------------------------
+        fwd_prologue(a, row, m, xt, kSave);
+        fence_proxy_async();
+        mbar_arrive(bar_act(t));
+        float sigma = head[640];
+        for (int g = 0; g < kNumGemms; ++g) {
+          mbar_wait(bar_acc(t), acc_ph, 400 + t);
+          acc_ph ^= 1;
+          tc_fence_after();
+          if (g < 9) {
+            __nv_bfloat16* sv = (kSave && valid) ? a.act + ((int64_t)g * a.M + row) * 256 : nullptr;
+            uint32_t* mk = (kSave && valid && g < 8) ? a.mask + ((int64_t)g * a.M + row) * 8 : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+              uint32_t r[32];
+              tmem_ld32(taddr + c0, r);
+              tmem_ld_wait();
+              if (g == 7) {                              // sigma head from fp32 post-ReLU activations (model.py:69)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), head[c0 + j], sigma);
+              }
+              if (kSave && mk != nullptr) mk[c0 >> 5] = relu_mask32(r);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint4 o;
+                if (g != 8) {                            // ReLU on every trunk layer (model.py:65); bottleneck has none (:70)
+                  o.x = pack_bf16x2_relu(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
+                  o.y = pack_bf16x2_relu(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                  o.z = pack_bf16x2_relu(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+                  o.w = pack_bf16x2_relu(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+                } else {
+                  o.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
+                  o.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                  o.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+                  o.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+                }
+                const int k = c0 + 8 * c;
+                *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
+                if (kSave && sv != nullptr) *reinterpret_cast<uint4*>(sv + k) = o;
+              }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(bar_act(t));
+          } else {
+            // view layer epilogue: + view bias, ReLU (model.py:73-74), rgb head (:75), output [rgb, sigma] (:77)
+            const int64_t vrow = (valid ? row : (a.M - 1)) / a.vb_div;
+            const float4* vb4 = reinterpret_cast<const float4*>(a.vb + vrow * 128);
+            __nv_bfloat16* sv = (kSave && valid) ? a.hv + row * 128 : nullptr;
+            float o0 = head[641], o1 = head[642], o2 = head[643];
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+              uint32_t r[32];
+              tmem_ld32(taddr + c0, r);
+              tmem_ld_wait();
+              float h[32];
+              uint32_t mw = 0;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b = __ldg(vb4 + (c0 >> 2) + j4);
+                h[4 * j4 + 0] = fmaxf(__uint_as_float(r[4 * j4 + 0]) + b.x, 0.f);
+                h[4 * j4 + 1] = fmaxf(__uint_as_float(r[4 * j4 + 1]) + b.y, 0.f);
+                h[4 * j4 + 2] = fmaxf(__uint_as_float(r[4 * j4 + 2]) + b.z, 0.f);
+                h[4 * j4 + 3] = fmaxf(__uint_as_float(r[4 * j4 + 3]) + b.w, 0.f);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                o0 = fmaf(h[j], head[256 + c0 + j], o0);
+                o1 = fmaf(h[j], head[384 + c0 + j], o1);
+                o2 = fmaf(h[j], head[512 + c0 + j], o2);
+                if (kSave) mw |= (h[j] > 0.f) ? (1u << j) : 0u;
+              }
+              if (kSave && sv != nullptr) {
+                a.hvmask[row * 4 + (c0 >> 5)] = mw;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  uint4 o;
+                  o.x = pack_bf16x2(h[8 * c + 0], h[8 * c + 1]);
+                  o.y = pack_bf16x2(h[8 * c + 2], h[8 * c + 3]);
+                  o.z = pack_bf16x2(h[8 * c + 4], h[8 * c + 5]);
+                  o.w = pack_bf16x2(h[8 * c + 6], h[8 * c + 7]);
+                  *reinterpret_cast<uint4*>(sv + c0 + 8 * c) = o;
+                }
+              }
+            }
+            if (valid) *reinterpret_cast<float4*>(a.out + row * 4) = make_float4(o0, o1, o2, sigma);
+            tc_fence_before();
+          }
+        }
+      } else {
+        // ------------------------------ dgrad chain ------------------------------
+        // prologue: d_hv_pre = (d_rgb . W_rgb) * [hv > 0]  (reference autograd of model.py:73-75)
+        const float4 dr = valid ? __ldg(reinterpret_cast<const float4*>(a.d_raw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+          uint4 mw = valid ? __ldg(reinterpret_cast<const uint4*>(a.hvmask) + row) : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t mws[4] = {mw.x, mw.y, mw.z, mw.w};
+          __nv_bfloat16* sv = valid ? a.dhv + row * 128 : nullptr;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int n = 8 * c + j;
+              const float g = fmaf(dr.x, head[256 + n], fmaf(dr.y, head[384 + n], dr.z * head[512 + n]));
+              v[j] = ((mws[n >> 5] >> (n & 31)) & 1u) ? g : 0.f;
+            }
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            const int k = 8 * c;
+            *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
+            if (sv != nullptr) *reinterpret_cast<uint4*>(sv + k) = o;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_act(t));
+        for (int g = 0; g < kNumGemms; ++g) {
+          // g = 0: d_bott (no mask) | g = 1: d_h7 (+ sigma term, mask 7) | g >= 2: d_pre_{8-g} (mask 8-g)
+          const int ml = 8 - g;                                    // mask layer (g >= 1)
+          uint4 m0 = make_uint4(~0u, ~0u, ~0u, ~0u), m1 = m0;
+          if (g >= 1) {                                            // prefetch the ReLU mask before the accumulator wait
+            const uint4* mp = reinterpret_cast<const uint4*>(a.mask + ((int64_t)ml * a.M + (valid ? row : 0)) * 8);
+            m0 = __ldg(mp); m1 = __ldg(mp + 1);
+          }
+          const uint32_t mws[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          const int dst = (g == 0) ? 8 : ml;                        // dpre slot: 8 = d_bott, else layer index
+          __nv_bfloat16* sv = valid ? a.dpre + ((int64_t)dst * a.M + row) * 256 : nullptr;
+          mbar_wait(bar_acc(t), acc_ph, 400 + t);
+          acc_ph ^= 1;
+          tc_fence_after();
 #pragma unroll 1
           for (int c0 = 0; c0 < 256; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(taddr + c0, r);
             tmem_ld_wait();
-            if (g == 7) {                              // sigma head from fp32 post-ReLU activations (model.py:69)
+            const uint32_t mw = mws[c0 >> 5];
+            float v[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), head[c0 + j], sigma);
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(r[j]);
+              if (g == 1) x = fmaf(dr.w, head[c0 + j], x);          // + d_sigma * w_sigma  (model.py:69)
+              v[j] = ((mw >> j) & 1u) ? x : 0.f;
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint4 o;
-              if (g != 8) {                            // ReLU on every trunk layer (model.py:65); bottleneck has none (:70)
-                o.x = pack_bf16x2_relu(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
-                o.y = pack_bf16x2_relu(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
-                o.z = pack_bf16x2_relu(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
-                o.w = pack_bf16x2_relu(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
-              } else {
-                o.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
-                o.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
-                o.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
-                o.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
-              }
+              o.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]); o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+              o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
               const int k = c0 + 8 * c;
-              *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
+              if (g < kNumGemms - 1) *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
               if (sv != nullptr) *reinterpret_cast<uint4*>(sv + k) = o;
             }
           }
           tc_fence_before();
-          fence_proxy_async();
-          mbar_arrive(bar_act(t));
-        } else {
-          // view layer epilogue: + view bias, ReLU (model.py:73-74), rgb head (:75), output [rgb, sigma] (:77)
-          const int64_t vrow = (valid ? row : (a.M - 1)) / a.vb_div;
-          const float4* vb4 = reinterpret_cast<const float4*>(a.vb + vrow * 128);
-          __nv_bfloat16* sv = (a.save != nullptr && valid) ? a.save + (int64_t)9 * a.M * 256 + row * 128 : nullptr;
-          float o0 = head[641], o1 = head[642], o2 = head[643];
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(taddr + c0, r);
-            tmem_ld_wait();
-            float h[32];
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b = __ldg(vb4 + (c0 >> 2) + j4);
-              h[4 * j4 + 0] = fmaxf(__uint_as_float(r[4 * j4 + 0]) + b.x, 0.f);
-              h[4 * j4 + 1] = fmaxf(__uint_as_float(r[4 * j4 + 1]) + b.y, 0.f);
-              h[4 * j4 + 2] = fmaxf(__uint_as_float(r[4 * j4 + 2]) + b.z, 0.f);
-              h[4 * j4 + 3] = fmaxf(__uint_as_float(r[4 * j4 + 3]) + b.w, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              o0 = fmaf(h[j], head[256 + c0 + j], o0);
-              o1 = fmaf(h[j], head[384 + c0 + j], o1);
-              o2 = fmaf(h[j], head[512 + c0 + j], o2);
-            }
-            if (sv != nullptr) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint4 o;
-                o.x = pack_bf16x2(h[8 * c + 0], h[8 * c + 1]);
-                o.y = pack_bf16x2(h[8 * c + 2], h[8 * c + 3]);
-                o.z = pack_bf16x2(h[8 * c + 4], h[8 * c + 5]);
-                o.w = pack_bf16x2(h[8 * c + 6], h[8 * c + 7]);
-                *reinterpret_cast<uint4*>(sv + c0 + 8 * c) = o;
-              }
-            }
+          if (g < kNumGemms - 1) {
+            fence_proxy_async();
+            mbar_arrive(bar_act(t));
           }
-          if (valid) *reinterpret_cast<float4*>(a.out + row * 4) = make_float4(o0, o1, o2, sigma);
-          tc_fence_before();
         }
       }
     }
@@ -514,21 +576,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs a
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-size_t mlp_tc_workspace_bytes(int64_t M, int save) {
-  size_t b = (size_t)M * 128 * sizeof(float);                 // view bias (upper bound: one row per sample)
-  if (save) b += (size_t)M * (9 * 256 + 128) * sizeof(__nv_bfloat16);
-  return b;
-}
+size_t mlp_tc_workspace_bytes(int64_t M, int save) { return ws_layout(M, save).total; }
 
-int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float coord_scale,
-                   const float* x_enc, const float* d_enc, int64_t M, const float* params, const void* packed,
-                   float* out, void* ws, size_t ws_bytes, int save, cudaStream_t st) {
-  NERF_CHECK_ARG(ws_bytes >= mlp_tc_workspace_bytes(M, save), "mlp tc forward: workspace too small (%zu < %zu)",
-                 ws_bytes, mlp_tc_workspace_bytes(M, save));
-  NERF_CHECK_ARG((((uintptr_t)packed | (uintptr_t)out | (uintptr_t)ws) & 15) == 0, "mlp tc forward: packed/out/workspace must be 16-byte aligned");
-  int rc = upload_schedule();
-  if (rc) return rc;
-  static int sm_count = 0;
+static int sm_count_cached = 0;
+template <bool kBwd, bool kSave>
+static int launch_tc(const TcArgs& a, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     int dev = 0;
@@ -536,31 +588,60 @@ int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals
     cudaDeviceProp p;
     NERF_CUDA(cudaGetDeviceProperties(&p, dev));
     NERF_CHECK_ARG(p.major == 10, "libnerf_b200 needs an sm_100 device (found sm_%d%d); there is no fallback", p.major, p.minor);
-    sm_count = p.multiProcessorCount;
-    NERF_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    sm_count_cached = p.multiProcessorCount;
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<kBwd, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done = true;
   }
-  float* vb = (float*)ws;
-  const int64_t nvb = (x_enc != nullptr) ? M : R;
-  view_bias_kernel<<<(unsigned)nvb, 128, 0, st>>>(rays_d, d_enc, nvb, params, vb);
-  NERF_LAUNCH_CHECK("view_bias_kernel");
-  FwdArgs a{};
-  a.rays_o = rays_o; a.rays_d = rays_d; a.z_vals = z_vals; a.S = S; a.coord_scale = coord_scale;
-  a.x_enc = x_enc; a.M = M; a.packed = (const uint8_t*)packed; a.params = params;
-  a.image_bytes = schedule().bytes; a.ncopies = num_copies();
-  a.vb = vb; a.vb_div = (x_enc != nullptr) ? 1 : S;
-  a.out = out;
-  a.save = save ? (__nv_bfloat16*)((uint8_t*)ws + (size_t)M * 128 * sizeof(float)) : nullptr;
-  a.num_pairs = ceil_div(M, 2 * kTileM);
-  const int grid = a.num_pairs < sm_count ? a.num_pairs : sm_count;
-  mlp_fwd_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
-  NERF_LAUNCH_CHECK("mlp_fwd_tc_kernel");
+  const int grid = a.num_pairs < sm_count_cached ? a.num_pairs : sm_count_cached;
+  mlp_tc_kernel<kBwd, kSave><<<grid, kThreads, kSmemBytes, st>>>(a);
+  NERF_LAUNCH_CHECK(kBwd ? "mlp_tc_kernel<dgrad>" : "mlp_tc_kernel<fwd>");
   return 0;
 }
 
-int mlp_tc_backward(const float*, int64_t, const float*, const void*, float*, void*, size_t, cudaStream_t) {
-  set_error("bf16 backward is not built yet");
-  return -2;
+static void fill_saved(TcArgs& a, void* ws, const WsLayout& L) {
+  uint8_t* b = (uint8_t*)ws;
+  a.act = (__nv_bfloat16*)(b + L.act); a.hv = (__nv_bfloat16*)(b + L.hv); a.xenc = (__nv_bfloat16*)(b + L.xenc);
+  a.mask = (uint32_t*)(b + L.mask); a.hvmask = (uint32_t*)(b + L.hvmask);
+  a.dpre = (__nv_bfloat16*)(b + L.dpre); a.dhv = (__nv_bfloat16*)(b + L.dhv);
+}
+
+int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float coord_scale,
+                   const float* x_enc, const float* d_enc, int64_t M, const float* params, const void* packed,
+                   float* out, void* ws, size_t ws_bytes, int save, cudaStream_t st) {
+  const WsLayout L = ws_layout(M, save);
+  NERF_CHECK_ARG(ws_bytes >= L.total, "mlp tc forward: workspace too small (%zu < %zu)", ws_bytes, L.total);
+  NERF_CHECK_ARG((((uintptr_t)packed | (uintptr_t)out | (uintptr_t)ws) & 15) == 0, "mlp tc forward: packed/out/workspace must be 16-byte aligned");
+  int rc = upload_schedule();
+  if (rc) return rc;
+  float* vb = (float*)((uint8_t*)ws + L.vb);
+  float* de = save ? (float*)((uint8_t*)ws + L.de) : nullptr;
+  const int64_t nvb = (x_enc != nullptr) ? M : R;
+  view_bias_kernel<<<(unsigned)nvb, 128, 0, st>>>(rays_d, d_enc, nvb, params, vb, de);
+  NERF_LAUNCH_CHECK("view_bias_kernel");
+  TcArgs a{};
+  a.rays_o = rays_o; a.rays_d = rays_d; a.z_vals = z_vals; a.S = S; a.coord_scale = coord_scale;
+  a.x_enc = x_enc; a.M = M; a.packed = (const uint8_t*)packed; a.params = params;
+  a.vb = vb; a.vb_div = (x_enc != nullptr) ? 1 : S;
+  a.out = out;
+  if (save) fill_saved(a, ws, L);
+  a.num_pairs = ceil_div(M, 2 * kTileM);
+  return save ? launch_tc<false, true>(a, st) : launch_tc<false, false>(a, st);
+}
+
+int mlp_tc_backward(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
+                    float* grads, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const WsLayout L = ws_layout(M, 1);
+  NERF_CHECK_ARG(ws_bytes >= L.total, "mlp tc backward: workspace too small (%zu < %zu)", ws_bytes, L.total);
+  NERF_CHECK_ARG(rows_per_dir >= 1, "mlp tc backward: rows_per_dir must be >= 1");
+  NERF_CHECK_ARG((((uintptr_t)d_raw | (uintptr_t)ws) & 15) == 0, "mlp tc backward: d_raw/workspace must be 16-byte aligned");
+  int rc = upload_schedule();
+  if (rc) return rc;
+  TcArgs a{};
+  a.d_raw = d_raw; a.M = M; a.packed = (const uint8_t*)packed; a.params = params;
+  fill_saved(a, ws, L);
+  a.num_pairs = ceil_div(M, 2 * kTileM);
+  if ((rc = launch_tc<true, false>(a, st))) return rc;                       // d(pre-activations) -> workspace
+  return mlp_tc_wgrad(ws, L, d_raw, M, rows_per_dir, grads, st);            // weight / bias gradients
 }
 
 }  // namespace nerf

@@ -1,0 +1,86 @@
+// Definitions shared by the tensor-core MLP kernels (forward, dgrad chain, wgrad): swizzled
+// shared-memory layouts, the weight-slot schedules and the bf16-mode workspace layout.
+#pragma once
+#include "nerf_common.cuh"
+#include "tc_ptx.cuh"
+
+#ifndef NERF_TC_NK
+#define NERF_TC_NK 2          // K-steps (16 wide) per weight slot
+#endif
+#ifndef NERF_TC_RING
+#define NERF_TC_RING 3        // ring slots
+#endif
+#ifndef NERF_TC_SKEW
+#define NERF_TC_SKEW 1        // slots by which tile B's issuer starts behind tile A's
+#endif
+
+namespace nerf {
+
+constexpr int kNK = NERF_TC_NK;
+constexpr int kRing = NERF_TC_RING;
+constexpr int kSkew = NERF_TC_SKEW;
+static_assert(kNK == 1 || kNK == 2, "slot = 1 or 2 K-steps");
+static_assert(kSkew >= 1 && kSkew + 1 < kRing, "ring must hold the skew plus at least one prefetch slot");
+constexpr int kSlotBytes = 8192 * kNK;            // 256 rows x 32 B x NK
+constexpr int kTileM = 128;
+
+// ---- swizzled K-major element offsets (bytes): 16-byte chunk index XOR row bits, as applied by
+// TMA / UMMA for SWIZZLE_{32,64,128}B ------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {   // rows of 128 B (64 bf16)
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ row) & 7) << 4) + (k & 7) * 2);
+}
+__host__ __device__ __forceinline__ uint32_t sw64_off(int row, int k) {    // rows of 64 B (32 bf16)
+  return (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((((k >> 3) ^ (row >> 1)) & 3) << 4) + (k & 7) * 2);
+}
+__host__ __device__ __forceinline__ uint32_t sw32_off(int row, int k) {    // rows of 32 B (16 bf16)
+  return (uint32_t)((row >> 3) * 256 + (row & 7) * 32 + ((((k >> 3) ^ (row >> 2)) & 1) << 4) + (k & 7) * 2);
+}
+
+// ---- weight-slot schedule ----------------------------------------------------------------------
+enum AKind : uint32_t { A_X = 0, A_ACT = 1, A_ONES = 2 };
+struct Slot {            // consumed by the kernels: one 16-byte constant-bank load per slot
+  uint32_t goff, bytes;
+  uint32_t a_add;        // (byte offset of the first K-step inside the A tile) >> 4
+  uint32_t flags;        // bits 0-1 a_kind | 2 nk==2 | 3 first | 4 last | 5 N==128
+};
+constexpr uint32_t kFlagNk2 = 4, kFlagFirst = 8, kFlagLast = 16, kFlagN128 = 32;
+struct PackSlot {        // consumed by the pack kernel: value(n,kk) = params[w_base + n*n_stride + kk*k_stride]
+  uint32_t goff;
+  int32_t w_base, n_stride, k_stride, kvalid, b_off, n, nk, sw, is_bias;
+};
+constexpr int kMaxSlots = 192;
+
+// ---- bf16-mode workspace (byte offsets) -----------------------------------------------------------
+// forward:  vb   fp32 [nvb][128]   view bias (one row per ray, or per sample for the encoded entry)
+//           de   fp32 [nvb][32]    encoded view direction (27 used)                     (save only)
+//           act  bf16 [9][M][256]  h0..h7 (post-ReLU), bottleneck                        (save only)
+//           hv   bf16 [M][128]     view-layer output (post-ReLU)                         (save only)
+//           xenc bf16 [M][64]      encoded position (63 used)                            (save only)
+//           mask u32  [8][M][8]    ReLU masks of h0..h7; hvmask u32 [M][4]               (save only)
+// backward: dpre bf16 [9][M][256]  d(pre-activation) of layers 0..7, d(bottleneck); dhv bf16 [M][128]
+struct WsLayout {
+  size_t vb, de, act, hv, xenc, mask, hvmask, dpre, dhv, total;
+};
+inline WsLayout ws_layout(int64_t M, int save) {
+  WsLayout w{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+  w.vb = take((size_t)M * 128 * 4);
+  if (save) {
+    w.de = take((size_t)M * 32 * 4);
+    w.act = take((size_t)9 * M * 256 * 2);
+    w.hv = take((size_t)M * 128 * 2);
+    w.xenc = take((size_t)M * 64 * 2);
+    w.mask = take((size_t)8 * M * 8 * 4);
+    w.hvmask = take((size_t)M * 4 * 4);
+    w.dpre = take((size_t)9 * M * 256 * 2);
+    w.dhv = take((size_t)M * 128 * 2);
+  }
+  w.total = o;
+  return w;
+}
+
+int mlp_tc_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t M, int rows_per_dir, float* grads,
+                 cudaStream_t st);
+
+}  // namespace nerf

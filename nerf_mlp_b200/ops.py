@@ -158,12 +158,34 @@ def mlp_fwd_encoded(model, x_enc, d_enc, precision, save):
     return out, (ws if save else None)
 
 
-def mlp_bwd(model, d_raw, ws, precision, flat_grads):
+def mlp_bwd(model, d_raw, ws, precision, flat_grads, rows_per_dir):
     _lib.require_cuda(d_raw, flat_grads)
     M = d_raw.numel() // 4
     packed = model.packed_weights() if precision == PREC_BF16 else None
-    check(dll().nerf_mlp_bwd(ptr(d_raw), M, ptr(model.flat_params), ptr(packed), ptr(flat_grads), ptr(ws),
-                             ws.numel(), int(precision), stream_ptr(d_raw.device)), "nerf_mlp_bwd")
+    check(dll().nerf_mlp_bwd(ptr(d_raw), M, int(rows_per_dir), ptr(model.flat_params), ptr(packed), ptr(flat_grads),
+                             ptr(ws), ws.numel(), int(precision), stream_ptr(d_raw.device)), "nerf_mlp_bwd")
+
+
+def bf16_workspace_views(ws, M):
+    """Typed views of the bf16-mode MLP workspace written by a forward with save=1 and by the
+    backward (layout: csrc/tc_common.cuh ws_layout).  For tests and debugging."""
+    def al(n):
+        return (n + 255) & ~255
+    out, off = {}, 0
+    for name, nbytes, dt, shape in (("vb", M * 128 * 4, torch.float32, (M, 128)),
+                                    ("de", M * 32 * 4, torch.float32, (M, 32)),
+                                    ("act", 9 * M * 256 * 2, torch.bfloat16, (9, M, 256)),
+                                    ("hv", M * 128 * 2, torch.bfloat16, (M, 128)),
+                                    ("xenc", M * 64 * 2, torch.bfloat16, (M, 64)),
+                                    ("mask", 8 * M * 8 * 4, torch.int32, (8, M, 8)),
+                                    ("hvmask", M * 4 * 4, torch.int32, (M, 4)),
+                                    ("dpre", 9 * M * 256 * 2, torch.bfloat16, (9, M, 256)),
+                                    ("dhv", M * 128 * 2, torch.bfloat16, (M, 128))):
+        out[name] = ws[off:off + nbytes].view(dt).view(shape)
+        off += al(nbytes)
+    if off != ws.numel():
+        raise RuntimeError(f"workspace size {ws.numel()} does not match the save layout for M={M} ({off})")
+    return out
 
 
 def _param_grads(model, run_bwd):
@@ -205,7 +227,8 @@ class RenderPassFn(torch.autograd.Function):
         d_rgb = _cg(d_rgb) if d_rgb is not None else torch.zeros_like(d)
         d_raw = composite_bwd(raw, z, d, ctx.noise, ctx.white, d_rgb, _cg(d_depth), _cg(d_acc), None)
         model, ws, prec = ctx.model, ctx.ws, ctx.precision
-        grads = _param_grads(model, lambda flat: mlp_bwd(model, d_raw, ws, prec, flat))
+        S = z.shape[1]
+        grads = _param_grads(model, lambda flat: mlp_bwd(model, d_raw, ws, prec, flat, S))
         ctx.ws = None
         return (None,) * 9 + tuple(grads)
 
@@ -225,7 +248,7 @@ class MLPEncodedFn(torch.autograd.Function):
             raise RuntimeError("MLPEncodedFn.backward: forward ran without saving activations")
         model, ws, prec = ctx.model, ctx.ws, ctx.precision
         d_out = _cg(d_out)
-        grads = _param_grads(model, lambda flat: mlp_bwd(model, d_out, ws, prec, flat))
+        grads = _param_grads(model, lambda flat: mlp_bwd(model, d_out, ws, prec, flat, 1))
         ctx.ws = None
         return (None,) * 5 + tuple(grads)
 
