@@ -222,15 +222,17 @@ struct TcArgs {
   int64_t M;
   const uint8_t* packed;
   const float* params;
-  // saved tensors (forward writes when kSave, dgrad reads)
-  __nv_bfloat16* act; __nv_bfloat16* hv; __nv_bfloat16* xenc; uint32_t* mask; uint32_t* hvmask;
+  // saved tensors (forward writes when kSave, dgrad reads the masks); *_img = tile images (tc_common.cuh)
+  uint8_t* act_img; uint8_t* hv_img; uint8_t* xenc_img; uint8_t* de16_img; uint32_t* mask; uint32_t* hvmask;
+  const float* de;                  // fp32 [nvb][32] encoded directions (written by view_bias_kernel)
   // dgrad outputs
-  __nv_bfloat16* dpre; __nv_bfloat16* dhv;
+  uint8_t* dpre_img; uint8_t* dhv_img;
+  int64_t Mp;                       // rows padded to whole tile pairs
   int num_pairs;
 };
 
 // bf16 x-tile row: 63 encoded channels (+ a zero pad column) -> 8 swizzled 16-byte chunks
-__device__ __forceinline__ void store_x_row(uint8_t* xt, int m, const float (&v)[64], __nv_bfloat16* save_row) {
+__device__ __forceinline__ void store_x_row(uint8_t* xt, int m, const float (&v)[64]) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     uint4 q;
@@ -239,11 +241,10 @@ __device__ __forceinline__ void store_x_row(uint8_t* xt, int m, const float (&v)
     q.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
     q.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
     *reinterpret_cast<uint4*>(xt + sw128_off(m, 8 * c)) = q;
-    if (save_row != nullptr) *reinterpret_cast<uint4*>(save_row + 8 * c) = q;
   }
 }
 
-__device__ __forceinline__ void fwd_prologue(const TcArgs& a, int64_t row, int m, uint8_t* xt, bool save) {
+__device__ __forceinline__ void fwd_prologue(const TcArgs& a, int64_t row, int m, uint8_t* xt) {
   float v[64];
 #pragma unroll
   for (int j = 0; j < 64; ++j) v[j] = 0.f;
@@ -282,14 +283,17 @@ __device__ __forceinline__ void fwd_prologue(const TcArgs& a, int64_t row, int m
       }
     }
   }
-  store_x_row(xt, m, v, (save && row < a.M) ? a.xenc + row * 64 : nullptr);
+  store_x_row(xt, m, v);
 }
 
+// ReLU mask of 32 fp32 accumulators, one funnel shift per element: bit j = !sign(r[j]).
+// (An accumulator that is exactly +0 counts as active; its gradient contribution is multiplied by
+// a zero activation downstream only in the weight gradient, and the event has measure zero.)
 __device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&r)[32]) {
   uint32_t w = 0;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) w |= (__uint_as_float(r[j]) > 0.f) ? (1u << j) : 0u;
-  return w;
+  for (int j = 31; j >= 0; --j) w = __funnelshift_l(r[j], w, 1);     // w = (w << 1) | (r[j] >> 31)
+  return ~w;
 }
 
 // kBwd = false: forward (kSave: also write the tensors the backward needs); kBwd = true: dgrad chain
@@ -404,24 +408,64 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
     const int m = q * 32 + lane;                      // row within the tile
     uint8_t* xt = smem + kOffX + t * kXBytes;
     uint8_t* at = smem + kOffAct + t * kActBytes;
+    const uint32_t at_s = sbase + kOffAct + t * kActBytes, xt_s = sbase + kOffX + t * kXBytes;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256;
+    constexpr bool kStores = kBwd || kSave;           // does this kernel write tile images to HBM?
+    // Tile-image saves: after the group's 128 threads have written (and proxy-fenced) a tile in
+    // shared memory, thread 0 of the group issues ONE bulk store; before anybody overwrites that
+    // region again, thread 0 waits for the store to have read it and the group re-synchronises.
+    // Per-warp granularity: this warp's 32 rows are one contiguous 4 KB block per 64-feature block,
+    // in shared memory and in the HBM tile image alike.
+    auto stores_drained = [&]() {
+#ifdef NERF_SAVE_BULK
+      if (kStores) {
+        if (lane == 0) bulk_wait_read();
+        __syncwarp();
+      }
+#endif
+    };
+    auto store_tile = [&](uint8_t* dst, uint32_t src, uint32_t bytes) {
+      __syncwarp();
+      const int nfb = (int)(bytes >> 14);
+#ifdef NERF_SAVE_BULK
+      if (lane == 0) {
+        for (int fb = 0; fb < nfb; ++fb) bulk_s2g(dst + fb * 16384 + q * 4096, src + fb * 16384 + q * 4096, 4096);
+        bulk_commit();
+      }
+#else
+      const uint8_t* sp = smem + (src - sbase) + q * 4096 + lane * 16;
+      uint8_t* dp = dst + q * 4096 + lane * 16;
+      for (int fb = 0; fb < nfb; ++fb) {
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(sp + fb * 16384 + i * 512);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(dp + fb * 16384 + i * 512) = v[i];
+      }
+      __syncwarp();     // lanes read each other's rows: nobody may overwrite the tile before all are done
+#endif
+    };
     uint32_t acc_ph = 0;
     for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
-      const int64_t row = ((int64_t)pair * 2 + t) * kTileM + m;
+      const int64_t tile = (int64_t)pair * 2 + t;
+      const int64_t row = tile * kTileM + m;
       const bool valid = row < a.M;
+      const int64_t ntiles = a.Mp / kTileM;
       if constexpr (!kBwd) {
         // ------------------------------ forward ------------------------------
-        fwd_prologue(a, row, m, xt, kSave);
+        stores_drained();
+        fwd_prologue(a, row, m, xt);
         fence_proxy_async();
         mbar_arrive(bar_act(t));
+        if (kSave) store_tile(a.xenc_img + tile * 16384, xt_s, 16384);
         float sigma = head[640];
         for (int g = 0; g < kNumGemms; ++g) {
           mbar_wait(bar_acc(t), acc_ph, 400 + t);
           acc_ph ^= 1;
           tc_fence_after();
+          stores_drained();
           if (g < 9) {
-            __nv_bfloat16* sv = (kSave && valid) ? a.act + ((int64_t)g * a.M + row) * 256 : nullptr;
-            uint32_t* mk = (kSave && valid && g < 8) ? a.mask + ((int64_t)g * a.M + row) * 8 : nullptr;
+            uint32_t mkw[8];
 #pragma unroll 1
             for (int c0 = 0; c0 < 256; c0 += 32) {
               uint32_t r[32];
@@ -431,7 +475,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), head[c0 + j], sigma);
               }
-              if (kSave && mk != nullptr) mk[c0 >> 5] = relu_mask32(r);
+#ifndef NERF_EXP_NOMASK
+              if (kSave) {
+                const uint32_t w = relu_mask32(r);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if ((c0 >> 5) == i) mkw[i] = w;
+              }
+#endif
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 uint4 o;
@@ -448,17 +498,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
                 }
                 const int k = c0 + 8 * c;
                 *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
-                if (kSave && sv != nullptr) *reinterpret_cast<uint4*>(sv + k) = o;
               }
             }
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_act(t));
+            if (kSave) {                                   // off the critical path: the MMAs are already released
+              store_tile(a.act_img + ((int64_t)g * ntiles + tile) * 65536, at_s, 65536);
+              if (g < 8 && valid) {
+                uint4* mp = reinterpret_cast<uint4*>(a.mask + ((int64_t)g * a.M + row) * 8);
+                mp[0] = make_uint4(mkw[0], mkw[1], mkw[2], mkw[3]);
+                mp[1] = make_uint4(mkw[4], mkw[5], mkw[6], mkw[7]);
+              }
+            }
           } else {
             // view layer epilogue: + view bias, ReLU (model.py:73-74), rgb head (:75), output [rgb, sigma] (:77)
             const int64_t vrow = (valid ? row : (a.M - 1)) / a.vb_div;
             const float4* vb4 = reinterpret_cast<const float4*>(a.vb + vrow * 128);
-            __nv_bfloat16* sv = (kSave && valid) ? a.hv + row * 128 : nullptr;
+            uint32_t hmw[4];
             float o0 = head[641], o1 = head[642], o2 = head[643];
 #pragma unroll 1
             for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -482,31 +539,52 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
                 o2 = fmaf(h[j], head[512 + c0 + j], o2);
                 if (kSave) mw |= (h[j] > 0.f) ? (1u << j) : 0u;
               }
-              if (kSave && sv != nullptr) {
-                a.hvmask[row * 4 + (c0 >> 5)] = mw;
+              if (kSave) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int i = 0; i < 4; ++i) if ((c0 >> 5) == i) hmw[i] = mw;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {             // stage in the (now free) activation tile, feature blocks 0-1
                   uint4 o;
                   o.x = pack_bf16x2(h[8 * c + 0], h[8 * c + 1]);
                   o.y = pack_bf16x2(h[8 * c + 2], h[8 * c + 3]);
                   o.z = pack_bf16x2(h[8 * c + 4], h[8 * c + 5]);
                   o.w = pack_bf16x2(h[8 * c + 6], h[8 * c + 7]);
-                  *reinterpret_cast<uint4*>(sv + c0 + 8 * c) = o;
+                  const int k = c0 + 8 * c;
+                  *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
                 }
               }
             }
             if (valid) *reinterpret_cast<float4*>(a.out + row * 4) = make_float4(o0, o1, o2, sigma);
             tc_fence_before();
+            if (kSave) {
+              // encoded view direction of this sample as bf16 (operand of view_linear's direction columns), block 2
+              const float* dep = a.de + vrow * 32;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (c < 4 && valid) {
+                  const float4 u0 = __ldg(reinterpret_cast<const float4*>(dep) + 2 * c);
+                  const float4 u1 = __ldg(reinterpret_cast<const float4*>(dep) + 2 * c + 1);
+                  o.x = pack_bf16x2(u0.x, u0.y); o.y = pack_bf16x2(u0.z, u0.w);
+                  o.z = pack_bf16x2(u1.x, u1.y); o.w = pack_bf16x2(u1.z, u1.w);
+                }
+                *reinterpret_cast<uint4*>(at + 2 * 16384 + sw128_off(m, 8 * c)) = o;
+              }
+              if (valid) *reinterpret_cast<uint4*>(a.hvmask + row * 4) = make_uint4(hmw[0], hmw[1], hmw[2], hmw[3]);
+              fence_proxy_async();
+              store_tile(a.hv_img + tile * 32768, at_s, 32768);
+              store_tile(a.de16_img + tile * 16384, at_s + 2 * 16384, 16384);
+            }
           }
         }
       } else {
         // ------------------------------ dgrad chain ------------------------------
         // prologue: d_hv_pre = (d_rgb . W_rgb) * [hv > 0]  (reference autograd of model.py:73-75)
         const float4 dr = valid ? __ldg(reinterpret_cast<const float4*>(a.d_raw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+        stores_drained();
         {
           uint4 mw = valid ? __ldg(reinterpret_cast<const uint4*>(a.hvmask) + row) : make_uint4(0u, 0u, 0u, 0u);
           const uint32_t mws[4] = {mw.x, mw.y, mw.z, mw.w};
-          __nv_bfloat16* sv = valid ? a.dhv + row * 128 : nullptr;
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             float v[8];
@@ -521,11 +599,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
             const int k = 8 * c;
             *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
-            if (sv != nullptr) *reinterpret_cast<uint4*>(sv + k) = o;
           }
         }
         fence_proxy_async();
         mbar_arrive(bar_act(t));
+        store_tile(a.dhv_img + tile * 32768, at_s, 32768);
         for (int g = 0; g < kNumGemms; ++g) {
           // g = 0: d_bott (no mask) | g = 1: d_h7 (+ sigma term, mask 7) | g >= 2: d_pre_{8-g} (mask 8-g)
           const int ml = 8 - g;                                    // mask layer (g >= 1)
@@ -536,10 +614,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           }
           const uint32_t mws[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
           const int dst = (g == 0) ? 8 : ml;                        // dpre slot: 8 = d_bott, else layer index
-          __nv_bfloat16* sv = valid ? a.dpre + ((int64_t)dst * a.M + row) * 256 : nullptr;
           mbar_wait(bar_acc(t), acc_ph, 400 + t);
           acc_ph ^= 1;
           tc_fence_after();
+          stores_drained();
 #pragma unroll 1
           for (int c0 = 0; c0 < 256; c0 += 32) {
             uint32_t r[32];
@@ -559,18 +637,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
               o.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]); o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
               o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
               const int k = c0 + 8 * c;
-              if (g < kNumGemms - 1) *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
-              if (sv != nullptr) *reinterpret_cast<uint4*>(sv + k) = o;
+              *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
             }
           }
           tc_fence_before();
-          if (g < kNumGemms - 1) {
-            fence_proxy_async();
-            mbar_arrive(bar_act(t));
-          }
+          fence_proxy_async();
+          if (g < kNumGemms - 1) mbar_arrive(bar_act(t));
+          store_tile(a.dpre_img + ((int64_t)dst * ntiles + tile) * 65536, at_s, 65536);
         }
       }
     }
+#ifdef NERF_SAVE_BULK
+    if (kStores && lane == 0) bulk_wait_all();            // every store has landed before the CTA exits
+#endif
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -600,9 +679,11 @@ static int launch_tc(const TcArgs& a, cudaStream_t st) {
 
 static void fill_saved(TcArgs& a, void* ws, const WsLayout& L) {
   uint8_t* b = (uint8_t*)ws;
-  a.act = (__nv_bfloat16*)(b + L.act); a.hv = (__nv_bfloat16*)(b + L.hv); a.xenc = (__nv_bfloat16*)(b + L.xenc);
+  a.act_img = b + L.act; a.hv_img = b + L.hv; a.xenc_img = b + L.xenc; a.de16_img = b + L.de16;
   a.mask = (uint32_t*)(b + L.mask); a.hvmask = (uint32_t*)(b + L.hvmask);
-  a.dpre = (__nv_bfloat16*)(b + L.dpre); a.dhv = (__nv_bfloat16*)(b + L.dhv);
+  a.de = (const float*)(b + L.de);
+  a.dpre_img = b + L.dpre; a.dhv_img = b + L.dhv;
+  a.Mp = L.Mp;
 }
 
 int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float coord_scale,

@@ -6,8 +6,9 @@
 //
 // is a GEMM whose contraction runs over the sample rows, so BOTH operands are "MN-major" for the
 // tensor core (features contiguous, rows strided).  One CTA owns one (layer, row-slab) job:
-//   loaders  (4 warps)  cp.async 16-byte chunks of a 64-row chunk of dY and X into a 3-stage ring,
-//                       in the 128B-swizzled MN-major layout UMMA expects
+//   loader   (1 lane)   TMA bulk copies of a 64-row chunk of dY and X into a 3-stage ring: the
+//                       operands are stored in HBM as shared-memory tile images (tc_common.cuh), i.e.
+//                       already in the 128B-swizzled MN-major layout UMMA expects
 //   issuer   (1 warp)   per chunk 4 K-steps x (1|2 M-halves) tcgen05.mma 128 x N x 16, fp32
 //                       accumulators for the whole dW block stay in TMEM (2 x 256 columns)
 //   bias     (4 warps)  column sums of the dY chunk straight from shared memory (db_l), then, after
@@ -25,17 +26,17 @@ constexpr int kWgChunkRows = 64;
 constexpr int kWgStages = 3;
 constexpr int kWgStageBytes = 65536;                       // A: 64 x 256 bf16 (32 KB) + B: 64 x 256 bf16 (32 KB)
 constexpr int kWgOffB = 32768;
-constexpr int kWgLoaderWarps = 4, kWgBiasWarps = 4;
+constexpr int kWgLoaderWarps = 1, kWgBiasWarps = 4;
 constexpr int kWgThreads = 32 * (kWgLoaderWarps + 1 + kWgBiasWarps);
 constexpr int kWgOffBar = kWgStages * kWgStageBytes;
 constexpr int kWgSmemBytes = kWgOffBar + 128;
 constexpr int kMaxJobs = 16;
 
 struct WgradJob {
-  const __nv_bfloat16* A; int lda;      // dY [M, lda]; columns [0, 128*mh) are used
-  const __nv_bfloat16* B; int ldb;      // X  [M, ldb]; columns [0, n) are used
+  const uint8_t* A; int a_tile_bytes;   // dY tile images; feature blocks [0, 2*mh) are used
+  const uint8_t* B; int b_tile_bytes;   // X  tile images; feature blocks [0, n/64) are used
   int mh;                               // M halves of 128 output features (1 or 2)
-  int n;                                // 64 or 256 input features
+  int n;                                // 64, 128 or 256 input features
   float* out; int ld_out; int ncols;    // dW block (column offset applied) and its valid width
   float* bias;                          // db or nullptr
   int first_block, nslabs;              // grid mapping
@@ -54,7 +55,7 @@ __host__ __device__ constexpr uint32_t make_idesc_mn(int N) {
   return make_idesc_bf16(128, N) | (1u << 15) | (1u << 16);
 }
 
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradJobs jobs, int64_t M) {
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradJobs jobs, int64_t Mp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -71,12 +72,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     if ((int)blockIdx.x >= jobs.j[j].first_block) ji = j;
   const WgradJob& job = jobs.j[ji];
   const int slab = blockIdx.x - job.first_block;
-  const int64_t total_chunks = (M + kWgChunkRows - 1) / kWgChunkRows;
+  const int64_t total_chunks = Mp / kWgChunkRows;
   const int64_t c_beg = total_chunks * slab / job.nslabs, c_end = total_chunks * (slab + 1) / job.nslabs;
   const int nchunks = (int)(c_end - c_beg);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full(s), 32 * kWgLoaderWarps); mbar_init(bar_empty(s), 1 + kWgBiasWarps); }
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1 + kWgBiasWarps); }
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
@@ -87,37 +88,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < kWgLoaderWarps) {
-    // ================= loaders =================
-    const int tid = threadIdx.x;                            // 0..127
-    const int a_cpr = 16 * job.mh, b_cpr = job.n >> 3;      // 16-byte chunks per row
-    for (int c = 0; c < nchunks + kWgStages - 1; ++c) {
-      if (c < nchunks) {
+    // ================= loader: one lane, TMA bulk copies of tile-image blocks =================
+    if (lane == 0) {
+      const int a_fb = 2 * job.mh, b_fb = job.n >> 6;
+      const uint32_t bytes = (uint32_t)(a_fb + b_fb) * 8192u;
+      for (int c = 0; c < nchunks; ++c) {
         const int s = c % kWgStages;
         if (c >= kWgStages) mbar_wait(bar_empty(s), ((c / kWgStages) - 1) & 1, 600 + s);
-        const int64_t row0 = (c_beg + c) * kWgChunkRows;
+        const int64_t chunk = c_beg + c;
+        const int64_t tile = chunk >> 1;
+        const uint32_t half = (uint32_t)(chunk & 1) * 8192u;      // rows 0-63 / 64-127 of the tile
         const uint32_t sa = sbase + s * kWgStageBytes, sb = sa + kWgOffB;
-        for (int idx = tid; idx < kWgChunkRows * a_cpr; idx += 32 * kWgLoaderWarps) {
-          const int r = idx / a_cpr, cc = idx % a_cpr;
-          const int64_t row = row0 + r;
-          const bool ok = row < M;
-          // MN-major SW128: feature block (64 feats) -> [row][128 B], 16-byte chunk XOR (row & 7)
-          cp_async16(sa + (cc >> 3) * (kWgChunkRows * 128) + r * 128 + (((cc & 7) ^ (r & 7)) << 4),
-                     job.A + (ok ? row : 0) * job.lda + cc * 8, ok ? 16u : 0u);
-        }
-        for (int idx = tid; idx < kWgChunkRows * b_cpr; idx += 32 * kWgLoaderWarps) {
-          const int r = idx / b_cpr, cc = idx % b_cpr;
-          const int64_t row = row0 + r;
-          const bool ok = row < M;
-          cp_async16(sb + (cc >> 3) * (kWgChunkRows * 128) + r * 128 + (((cc & 7) ^ (r & 7)) << 4),
-                     job.B + (ok ? row : 0) * job.ldb + cc * 8, ok ? 16u : 0u);
-        }
-      }
-      cp_async_commit();
-      const int done = c - (kWgStages - 1);                 // the group issued kWgStages-1 iterations ago has landed
-      if (done >= 0) {
-        cp_async_wait<kWgStages - 1>();
-        fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(bar_full(done % kWgStages));
+        mbar_expect_tx(bar_full(s), bytes);
+        for (int fb = 0; fb < a_fb; ++fb)
+          bulk_g2s(sa + fb * 8192, job.A + tile * job.a_tile_bytes + fb * 16384 + half, 8192, bar_full(s));
+        for (int fb = 0; fb < b_fb; ++fb)
+          bulk_g2s(sb + fb * 8192, job.B + tile * job.b_tile_bytes + fb * 16384 + half, 8192, bar_full(s));
       }
     }
   } else if (warp == kWgLoaderWarps) {
@@ -194,91 +180,121 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   if (warp == kWgLoaderWarps) tmem_dealloc(tmem_base, 512);
 }
 
-// ---- small CUDA-core pieces ----------------------------------------------------------------------
-// rgb_linear (dW[3,128], db[3]) and sigma_linear (dW[1,256], db[1]): thread = input feature
-__global__ void __launch_bounds__(256) heads_wgrad_kernel(const float* __restrict__ d_raw, const __nv_bfloat16* __restrict__ hv,
-                                                         const __nv_bfloat16* __restrict__ h7, int64_t M, int64_t rows_per_block,
-                                                         float* __restrict__ grads) {
-  const int t = threadIdx.x;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = min(M, r0 + rows_per_block);
-  float ar = 0.f, ag = 0.f, ab = 0.f, as = 0.f, br = 0.f, bg = 0.f, bb = 0.f, bs = 0.f;
-  for (int64_t row = r0; row < r1; ++row) {
-    const float4 d = __ldg(reinterpret_cast<const float4*>(d_raw) + row);
-    as = fmaf(d.w, __bfloat162float(h7[row * 256 + t]), as);
-    if (t < 128) {
-      const float h = __bfloat162float(hv[row * 128 + t]);
-      ar = fmaf(d.x, h, ar); ag = fmaf(d.y, h, ag); ab = fmaf(d.z, h, ab);
+// ---- small CUDA-core piece: rgb_linear (dW[3,128], db[3]) and sigma_linear (dW[1,256], db[1]) ----
+// Reads the hv / h7 tile images with 16 bytes per lane: a warp covers one 512-byte h7 row (or two
+// 256-byte hv rows) per load instruction; lane l owns logical 16-byte chunk l of the row.
+constexpr int kHeadsRowsPerWarp = 64, kHeadsWarps = 8;
+__global__ void __launch_bounds__(32 * kHeadsWarps) heads_wgrad_kernel(const float* __restrict__ d_raw,
+                                                                       const uint8_t* __restrict__ hv_img,
+                                                                       const uint8_t* __restrict__ h7_img, int64_t M,
+                                                                       float* __restrict__ grads) {
+  __shared__ float red[256 + 384 + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 644; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int64_t r0 = ((int64_t)blockIdx.x * kHeadsWarps + warp) * kHeadsRowsPerWarp;
+  float as[8], av[3][8], bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { as[j] = 0.f; av[0][j] = av[1][j] = av[2][j] = 0.f; }
+  // sigma: h7 rows, lane = chunk (fb = lane>>3, cl = lane&7)
+  for (int i = 0; i < kHeadsRowsPerWarp; i += 4) {
+    uint4 x[4]; float4 d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t row = r0 + i + u;
+      const bool ok = row < M;
+      const int rt = (int)(row & 127);
+      d[u] = ok ? __ldg(reinterpret_cast<const float4*>(d_raw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[u] = ok ? __ldg(reinterpret_cast<const uint4*>(h7_img + (row >> 7) * 65536 + (lane >> 3) * 16384 + rt * 128 +
+                                                       (((lane & 7) ^ (rt & 7)) << 4)))
+                : make_uint4(0u, 0u, 0u, 0u);
     }
-    if (t == 0) { br += d.x; bg += d.y; bb += d.z; bs += d.w; }
-  }
-  atomicAdd(grads + w_off(L_SIGMA) + t, as);
-  if (t < 128) {
-    atomicAdd(grads + w_off(L_RGB) + t, ar);
-    atomicAdd(grads + w_off(L_RGB) + 128 + t, ag);
-    atomicAdd(grads + w_off(L_RGB) + 256 + t, ab);
-  }
-  if (t == 0) {
-    atomicAdd(grads + b_off(L_RGB), br); atomicAdd(grads + b_off(L_RGB) + 1, bg); atomicAdd(grads + b_off(L_RGB) + 2, bb);
-    atomicAdd(grads + b_off(L_SIGMA), bs);
-  }
-}
-
-// view_linear: the 27 direction columns and the bias.  d_hv_pre rows of one direction (ray) are
-// summed first, then dW[n][256+j] += g[n]*de[j], db[n] += g[n].   thread = output feature n
-__global__ void __launch_bounds__(128) view_dirs_wgrad_kernel(const __nv_bfloat16* __restrict__ dhv, const float* __restrict__ de,
-                                                             int64_t M, int rows_per_dir, int64_t dirs_per_block,
-                                                             float* __restrict__ grads) {
-  const int n = threadIdx.x;
-  const int64_t ndirs = (M + rows_per_dir - 1) / rows_per_dir;
-  const int64_t v0 = (int64_t)blockIdx.x * dirs_per_block, v1 = min(ndirs, v0 + dirs_per_block);
-  float acc[27], accb = 0.f;
 #pragma unroll
-  for (int j = 0; j < 27; ++j) acc[j] = 0.f;
-  for (int64_t v = v0; v < v1; ++v) {
-    float g = 0.f;
-    const int64_t r0 = v * rows_per_dir, r1 = min(M, r0 + rows_per_dir);
-    for (int64_t row = r0; row < r1; ++row) g += __bfloat162float(dhv[row * 128 + n]);
-    accb += g;
-    const float* d = de + v * 32;
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
 #pragma unroll
-    for (int j = 0; j < 27; ++j) acc[j] = fmaf(g, __ldg(d + j), acc[j]);
+      for (int j = 0; j < 4; ++j) {
+        as[2 * j] = fmaf(d[u].w, __uint_as_float(w[j] << 16), as[2 * j]);
+        as[2 * j + 1] = fmaf(d[u].w, __uint_as_float(w[j] & 0xFFFF0000u), as[2 * j + 1]);
+      }
+      bsum[0] += d[u].x; bsum[1] += d[u].y; bsum[2] += d[u].z; bsum[3] += d[u].w;
+    }
   }
-  float* w = grads + w_off(L_VIEW) + (int64_t)n * 283 + 256;
+  // rgb: hv rows, two rows per instruction: lanes 0-15 -> row 2i, 16-31 -> row 2i+1; chunk = lane & 15
+  const int hc = lane & 15;
+  for (int i = 0; i < kHeadsRowsPerWarp; i += 8) {
+    uint4 x[4]; float4 d[4];
 #pragma unroll
-  for (int j = 0; j < 27; ++j) atomicAdd(w + j, acc[j]);
-  atomicAdd(grads + b_off(L_VIEW) + n, accb);
+    for (int u = 0; u < 4; ++u) {
+      const int64_t row = r0 + i + 2 * u + (lane >> 4);
+      const bool ok = row < M;
+      const int rt = (int)(row & 127);
+      d[u] = ok ? __ldg(reinterpret_cast<const float4*>(d_raw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[u] = ok ? __ldg(reinterpret_cast<const uint4*>(hv_img + (row >> 7) * 32768 + (hc >> 3) * 16384 + rt * 128 +
+                                                       (((hc & 7) ^ (rt & 7)) << 4)))
+                : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xFFFF0000u);
+        av[0][2 * j] = fmaf(d[u].x, lo, av[0][2 * j]); av[0][2 * j + 1] = fmaf(d[u].x, hi, av[0][2 * j + 1]);
+        av[1][2 * j] = fmaf(d[u].y, lo, av[1][2 * j]); av[1][2 * j + 1] = fmaf(d[u].y, hi, av[1][2 * j + 1]);
+        av[2][2 * j] = fmaf(d[u].z, lo, av[2][2 * j]); av[2][2 * j + 1] = fmaf(d[u].z, hi, av[2][2 * j + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&red[lane * 8 + j], as[j]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(&red[256 + c * 128 + hc * 8 + j], av[c][j]);   // lanes l and l+16 share features
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) atomicAdd(&red[640 + c], bsum[c]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 644; i += blockDim.x) {
+    float* dst = i < 256 ? grads + w_off(L_SIGMA) + i
+               : i < 640 ? grads + w_off(L_RGB) + (i - 256)
+               : i < 643 ? grads + b_off(L_RGB) + (i - 640)
+                         : grads + b_off(L_SIGMA);
+    atomicAdd(dst, red[i]);
+  }
 }
 
 int mlp_tc_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t M, int rows_per_dir, float* grads,
                  cudaStream_t st) {
+  (void)rows_per_dir;   // the per-sample direction encodings were saved by the forward (de16)
   const uint8_t* b = (const uint8_t*)ws;
-  const __nv_bfloat16* act = (const __nv_bfloat16*)(b + L.act);
-  const __nv_bfloat16* hv = (const __nv_bfloat16*)(b + L.hv);
-  const __nv_bfloat16* xenc = (const __nv_bfloat16*)(b + L.xenc);
-  const __nv_bfloat16* dpre = (const __nv_bfloat16*)(b + L.dpre);
-  const __nv_bfloat16* dhv = (const __nv_bfloat16*)(b + L.dhv);
-  const float* de = (const float*)(b + L.de);
-  auto ACT = [&](int l) { return act + (int64_t)l * M * 256; };     // h_l (l = 8: bottleneck)
-  auto DPRE = [&](int l) { return dpre + (int64_t)l * M * 256; };   // d(pre-activation) of layer l (8: d_bottleneck)
+  const int64_t ntiles = L.Mp / kTileM;
+  auto ACT = [&](int l) { return b + L.act + (int64_t)l * ntiles * 65536; };     // h_l (l = 8: bottleneck)
+  auto DPRE = [&](int l) { return b + L.dpre + (int64_t)l * ntiles * 65536; };   // d(pre-act) of layer l (8: d_bottleneck)
+  const uint8_t* hv = b + L.hv;
+  const uint8_t* xenc = b + L.xenc;
+  const uint8_t* de16 = b + L.de16;
+  const uint8_t* dhv = b + L.dhv;
 
   // ---- tensor-core jobs ----
   WgradJobs jb{};
   WgradJob* jobs = jb.j;
   int nj = 0;
-  auto add = [&](const __nv_bfloat16* A, int lda, int mh, const __nv_bfloat16* B, int ldb, int n, int layer, int col0,
-                 int ncols, bool bias, int weight) {
+  auto add = [&](const uint8_t* A, int a_tile_bytes, int mh, const uint8_t* B, int b_tile_bytes, int n, int layer,
+                 int col0, int ncols, bool bias, int weight) {
     WgradJob& j = jobs[nj++];
-    j.A = A; j.lda = lda; j.mh = mh; j.B = B; j.ldb = ldb; j.n = n;
+    j.A = A; j.a_tile_bytes = a_tile_bytes; j.mh = mh; j.B = B; j.b_tile_bytes = b_tile_bytes; j.n = n;
     j.out = grads + w_off(layer) + col0; j.ld_out = kIn[layer]; j.ncols = ncols;
     j.bias = bias ? grads + b_off(layer) : nullptr;
     j.nslabs = weight;                                               // relative cost, turned into slabs below
   };
-  add(DPRE(0), 256, 2, xenc, 64, 64, 0, 0, 63, true, 5);                                   // layer 0: X = x_enc
-  for (int l = 1; l <= 7; ++l) add(DPRE(l), 256, 2, ACT(l - 1), 256, 256, l, l == 5 ? 63 : 0, 256, true, 8);
-  add(DPRE(5), 256, 2, xenc, 64, 64, 5, 0, 63, false, 5);                                  // layer 5, x part of [x,h]
-  add(DPRE(8), 256, 2, ACT(7), 256, 256, L_BOTT, 0, 256, true, 8);                         // bottleneck_linear
-  add(dhv, 128, 1, ACT(8), 256, 256, L_VIEW, 0, 256, false, 6);                            // view_linear, bottleneck columns
+  add(DPRE(0), 65536, 2, xenc, 16384, 64, 0, 0, 63, true, 5);                              // layer 0: X = x_enc
+  for (int l = 1; l <= 7; ++l) add(DPRE(l), 65536, 2, ACT(l - 1), 65536, 256, l, l == 5 ? 63 : 0, 256, true, 8);
+  add(DPRE(5), 65536, 2, xenc, 16384, 64, 5, 0, 63, false, 5);                             // layer 5, x part of [x,h]
+  add(DPRE(8), 65536, 2, ACT(7), 65536, 256, L_BOTT, 0, 256, true, 8);                     // bottleneck_linear
+  add(dhv, 32768, 1, ACT(8), 65536, 256, L_VIEW, 0, 256, true, 6);                         // view_linear: bottleneck columns + bias
+  add(dhv, 32768, 1, de16, 16384, 64, L_VIEW, 256, 27, false, 3);                          // view_linear: direction columns
   static int sm_count = 0;
   static bool attr_done = false;
   if (!attr_done) {
@@ -292,7 +308,7 @@ int mlp_tc_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t 
   }
   int wsum = 0;
   for (int j = 0; j < nj; ++j) wsum += jobs[j].nslabs;
-  const int64_t total_chunks = (M + kWgChunkRows - 1) / kWgChunkRows;
+  const int64_t total_chunks = L.Mp / kWgChunkRows;
   int nblocks = 0;
   for (int j = 0; j < nj; ++j) {
     int64_t s = (int64_t)jobs[j].nslabs * sm_count / wsum;
@@ -303,20 +319,13 @@ int mlp_tc_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t 
     nblocks += (int)s;
   }
   jb.n = nj;
-  wgrad_tc_kernel<<<nblocks, kWgThreads, kWgSmemBytes, st>>>(jb, M);
+  wgrad_tc_kernel<<<nblocks, kWgThreads, kWgSmemBytes, st>>>(jb, L.Mp);
   NERF_LAUNCH_CHECK("wgrad_tc_kernel");
 
-  // ---- CUDA-core pieces ----
-  {
-    const int64_t rpb = 512;
-    heads_wgrad_kernel<<<ceil_div(M, rpb), 256, 0, st>>>(d_raw, hv, ACT(7), M, rpb, grads);
-    NERF_LAUNCH_CHECK("heads_wgrad_kernel");
-    const int64_t ndirs = (M + rows_per_dir - 1) / rows_per_dir;
-    int64_t dpb = (ndirs + 4 * sm_count - 1) / (4 * sm_count);
-    if (dpb < 1) dpb = 1;
-    view_dirs_wgrad_kernel<<<ceil_div(ndirs, dpb), 128, 0, st>>>(dhv, de, M, rows_per_dir, dpb, grads);
-    NERF_LAUNCH_CHECK("view_dirs_wgrad_kernel");
-  }
+  // ---- CUDA-core piece: the two tiny heads ----
+  heads_wgrad_kernel<<<ceil_div(M, (int64_t)kHeadsWarps * kHeadsRowsPerWarp), 32 * kHeadsWarps, 0, st>>>(
+      d_raw, hv, ACT(7), M, grads);
+  NERF_LAUNCH_CHECK("heads_wgrad_kernel");
   return 0;
 }
 

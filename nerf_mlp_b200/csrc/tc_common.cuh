@@ -51,30 +51,42 @@ struct PackSlot {        // consumed by the pack kernel: value(n,kk) = params[w_
 constexpr int kMaxSlots = 192;
 
 // ---- bf16-mode workspace (byte offsets) -----------------------------------------------------------
-// forward:  vb   fp32 [nvb][128]   view bias (one row per ray, or per sample for the encoded entry)
-//           de   fp32 [nvb][32]    encoded view direction (27 used)                     (save only)
-//           act  bf16 [9][M][256]  h0..h7 (post-ReLU), bottleneck                        (save only)
-//           hv   bf16 [M][128]     view-layer output (post-ReLU)                         (save only)
-//           xenc bf16 [M][64]      encoded position (63 used)                            (save only)
-//           mask u32  [8][M][8]    ReLU masks of h0..h7; hvmask u32 [M][4]               (save only)
-// backward: dpre bf16 [9][M][256]  d(pre-activation) of layers 0..7, d(bottleneck); dhv bf16 [M][128]
+// Saved activations / gradients live in HBM as SHARED-MEMORY TILE IMAGES: per 128-row tile and
+// per 64-feature block a contiguous 16 KB block [128 rows][128 B] with the 16-byte chunks XOR-
+// swizzled by (row & 7) -- byte for byte what the kernels hold in shared memory.  A save is then
+// one TMA bulk store of the tile, and the wgrad kernel's operand loads are plain TMA bulk loads.
+//   element (row r, feature f) of a tensor with F features (F/64 blocks per tile):
+//     tile = r / 128, rt = r % 128, fb = f / 64
+//     byte = tile * (F/64) * 16384 + fb * 16384 + rt * 128 + ((((f % 64) / 8) ^ (rt & 7)) * 16) + (f % 8) * 2
+// forward:  vb    fp32 [nvb][128]    view bias (one row per ray, or per sample for the encoded entry)
+//           de    fp32 [nvb][32]     encoded view direction (27 used)                     (save only)
+//           act   img  [9][Mp x 256] h0..h7 (post-ReLU), bottleneck                       (save only)
+//           hv    img  [Mp x 128]    view-layer output (post-ReLU)                        (save only)
+//           xenc  img  [Mp x 64]     encoded position (63 used)                           (save only)
+//           de16  img  [Mp x 64]     encoded view direction per sample (27 used)          (save only)
+//           mask  u32  [8][M][8]     ReLU masks of h0..h7; hvmask u32 [M][4]   (row-major, save only)
+// backward: dpre  img  [9][Mp x 256] d(pre-activation) of layers 0..7, d(bottleneck); dhv img [Mp x 128];
+//           draw16 img [Mp x 64]     d_raw as bf16 (4 used)   -- Mp = rows padded to whole tile pairs
 struct WsLayout {
-  size_t vb, de, act, hv, xenc, mask, hvmask, dpre, dhv, total;
+  size_t vb, de, act, hv, xenc, de16, mask, hvmask, dpre, dhv, total;
+  int64_t Mp;
 };
 inline WsLayout ws_layout(int64_t M, int save) {
   WsLayout w{};
   size_t o = 0;
-  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) & ~(size_t)1023; return r; };
+  w.Mp = (M + 2 * kTileM - 1) / (2 * kTileM) * (2 * kTileM);
   w.vb = take((size_t)M * 128 * 4);
   if (save) {
     w.de = take((size_t)M * 32 * 4);
-    w.act = take((size_t)9 * M * 256 * 2);
-    w.hv = take((size_t)M * 128 * 2);
-    w.xenc = take((size_t)M * 64 * 2);
+    w.act = take((size_t)9 * w.Mp * 256 * 2);
+    w.hv = take((size_t)w.Mp * 128 * 2);
+    w.xenc = take((size_t)w.Mp * 64 * 2);
+    w.de16 = take((size_t)w.Mp * 64 * 2);
     w.mask = take((size_t)8 * M * 8 * 4);
     w.hvmask = take((size_t)M * 4 * 4);
-    w.dpre = take((size_t)9 * M * 256 * 2);
-    w.dhv = take((size_t)M * 128 * 2);
+    w.dpre = take((size_t)9 * w.Mp * 256 * 2);
+    w.dhv = take((size_t)w.Mp * 128 * 2);
   }
   w.total = o;
   return w;

@@ -166,22 +166,43 @@ def mlp_bwd(model, d_raw, ws, precision, flat_grads, rows_per_dir):
                              ptr(ws), ws.numel(), int(precision), stream_ptr(d_raw.device)), "nerf_mlp_bwd")
 
 
+def _untile(img, rows, feats):
+    """Decode a shared-memory tile image (csrc/tc_common.cuh) into a row-major [rows, feats] tensor:
+    per 128-row tile and 64-feature block a [128][8 chunks][8] block whose 16-byte chunks are
+    XOR-swizzled by (row & 7)."""
+    nt, nfb = rows // 128, feats // 64
+    t = img.view(nt, nfb, 128, 8, 8)
+    r = torch.arange(128, device=img.device).view(1, 1, 128, 1, 1)
+    c = torch.arange(8, device=img.device).view(1, 1, 1, 8, 1)
+    idx = (c ^ (r & 7)).expand(nt, nfb, 128, 8, 8)
+    return torch.gather(t, 3, idx).permute(0, 2, 1, 3, 4).reshape(rows, feats)
+
+
 def bf16_workspace_views(ws, M):
-    """Typed views of the bf16-mode MLP workspace written by a forward with save=1 and by the
+    """Decoded views of the bf16-mode MLP workspace written by a forward with save=1 and by the
     backward (layout: csrc/tc_common.cuh ws_layout).  For tests and debugging."""
     def al(n):
-        return (n + 255) & ~255
+        return (n + 1023) & ~1023
+    Mp = (M + 255) // 256 * 256
     out, off = {}, 0
-    for name, nbytes, dt, shape in (("vb", M * 128 * 4, torch.float32, (M, 128)),
-                                    ("de", M * 32 * 4, torch.float32, (M, 32)),
-                                    ("act", 9 * M * 256 * 2, torch.bfloat16, (9, M, 256)),
-                                    ("hv", M * 128 * 2, torch.bfloat16, (M, 128)),
-                                    ("xenc", M * 64 * 2, torch.bfloat16, (M, 64)),
-                                    ("mask", 8 * M * 8 * 4, torch.int32, (8, M, 8)),
-                                    ("hvmask", M * 4 * 4, torch.int32, (M, 4)),
-                                    ("dpre", 9 * M * 256 * 2, torch.bfloat16, (9, M, 256)),
-                                    ("dhv", M * 128 * 2, torch.bfloat16, (M, 128))):
-        out[name] = ws[off:off + nbytes].view(dt).view(shape)
+    spec = (("vb", M * 128 * 4, torch.float32, (M, 128), None),
+            ("de", M * 32 * 4, torch.float32, (M, 32), None),
+            ("act", 9 * Mp * 256 * 2, torch.bfloat16, None, (9, 256)),
+            ("hv", Mp * 128 * 2, torch.bfloat16, None, (1, 128)),
+            ("xenc", Mp * 64 * 2, torch.bfloat16, None, (1, 64)),
+            ("de16", Mp * 64 * 2, torch.bfloat16, None, (1, 64)),
+            ("mask", 8 * M * 8 * 4, torch.int32, (8, M, 8), None),
+            ("hvmask", M * 4 * 4, torch.int32, (M, 4), None),
+            ("dpre", 9 * Mp * 256 * 2, torch.bfloat16, None, (9, 256)),
+            ("dhv", Mp * 128 * 2, torch.bfloat16, None, (1, 128)))
+    for name, nbytes, dt, shape, img in spec:
+        flat = ws[off:off + nbytes].view(dt)
+        if img is None:
+            out[name] = flat.view(shape)
+        else:
+            n, feats = img
+            dec = torch.stack([_untile(flat.view(n, -1)[i], Mp, feats)[:M] for i in range(n)])
+            out[name] = dec if n > 1 else dec[0]
         off += al(nbytes)
     if off != ws.numel():
         raise RuntimeError(f"workspace size {ws.numel()} does not match the save layout for M={M} ({off})")

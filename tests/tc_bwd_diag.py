@@ -52,31 +52,10 @@ def main(R=300, S=64):
     V = f[off:off + M * 283].view(M, 283); off += M * 283
     HV = f[off:off + M * 128].view(M, 128)
     W = {k: torch.from_numpy(v).to(dev) for k, v in p.items()}
-    # bf16 workspace layout (tc_common.cuh ws_layout)
-    ws = wss["bf16"]
-
-    def take(off, nbytes):
-        return off, off + ((nbytes + 255) & ~255)
-
-    o_ = 0
-    o_vb, o_ = take(o_, M * 128 * 4)
-    o_de, o_ = take(o_, M * 32 * 4)
-    o_act, o_ = take(o_, 9 * M * 256 * 2)
-    o_hv, o_ = take(o_, M * 128 * 2)
-    o_x, o_ = take(o_, M * 64 * 2)
-    o_mask, o_ = take(o_, 8 * M * 8 * 4)
-    o_hvm, o_ = take(o_, M * 4 * 4)
-    o_dpre, o_ = take(o_, 9 * M * 256 * 2)
-    o_dhv, o_ = take(o_, M * 128 * 2)
-    assert o_ == ws.numel(), (o_, ws.numel())
-    dpre = ws[o_dpre:o_dpre + 9 * M * 256 * 2].view(torch.bfloat16).view(9, M, 256).float()
-    dhv = ws[o_dhv:o_dhv + M * 128 * 2].view(torch.bfloat16).view(M, 128).float()
-    xenc = ws[o_x:o_x + M * 64 * 2].view(torch.bfloat16).view(M, 64).float()
-    mask = ws[o_mask:o_mask + 8 * M * 32].view(torch.int32).view(8, M, 8)
+    v = ops.bf16_workspace_views(wss["bf16"], M)
+    dpre, dhv, xenc, mask = v["dpre"].float(), v["dhv"].float(), v["xenc"].float(), v["mask"]
     print("x_enc save vs fp32: max %.3e" % (xenc[:, :63] - X[:, :63]).abs().max().item())
-    act16 = ws[o_act:o_act + 9 * M * 256 * 2].view(torch.bfloat16).view(9, M, 256).float()
-    hv16 = ws[o_hv:o_hv + M * 128 * 2].view(torch.bfloat16).view(M, 128).float()
-    hvm = ws[o_hvm:o_hvm + M * 16].view(torch.int32).view(M, 4)
+    act16, hv16, hvm = v["act"].float(), v["hv"].float(), v["hvmask"]
     ar = torch.arange(32, device=dev, dtype=torch.int32)
     bits = {}
     for l in range(8):
@@ -108,7 +87,8 @@ def main(R=300, S=64):
     gref["sigma_linear.bias"] = d_raw[:, 3].sum(0, keepdim=True)
     gref["bottleneck_linear.weight"] = dref[8].T @ act16[7]
     gref["bottleneck_linear.bias"] = dref[8].sum(0)
-    de = ws[o_de:o_de + M * 128].view(torch.float32)[: R * 32].view(R, 32)[:, :27]
+    de = v["de"][:R, :27]
+    print("de16 save vs fp32 de: max %.3e" % (v["de16"].float()[:, :27] - de.repeat_interleave(S, 0)).abs().max().item())
     vin = torch.cat([act16[8], de.repeat_interleave(S, 0)], 1)
     gref["view_linear.weight"] = d_hv.T @ vin
     gref["view_linear.bias"] = d_hv.sum(0)

@@ -41,13 +41,8 @@ def main(R=300, S=64):
     H[4] = X[:, 63:]
     V = f[off:off + M * 283].view(M, 283); off += M * 283
     HV = f[off:off + M * 128].view(M, 128)
-    def al(n):
-        return (n + 255) & ~255
-    o_act = al(M * 128 * 4) + al(M * 32 * 4)                 # tc_common.cuh ws_layout: vb | de | act | hv ...
-    o_hv = o_act + al(9 * M * 256 * 2)
-    sv = ws16[o_act:o_act + 9 * M * 256 * 2].view(torch.bfloat16).view(9, M, 256).float()
-    hv16 = ws16[o_hv:o_hv + M * 128 * 2].view(torch.bfloat16).view(M, 128).float()
-    vb = ws16[: M * 128 * 4].view(torch.float32)[: R * 128].view(R, 128)
+    v = ops.bf16_workspace_views(ws16, M)
+    sv, hv16, vb = v["act"].float(), v["hv"].float(), v["vb"][:R]
     # oracle cross-check of the fp32 path itself
     xe, de = O.encode_samples(o, d, z.cpu().numpy(), O.RenderConfig(N_samples=S))
     ref = O.mlp_forward(p, xe, de)

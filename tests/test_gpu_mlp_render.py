@@ -14,7 +14,7 @@ Tolerance rules (written down before the first measurement):
 
   bf16 tensor-core mode
     * MLP raw outputs: <= 2e-2 abs vs the fp32 oracle (256-wide bf16 layers, fp32 accumulate).
-    * maps: rays whose last-sample sigma is within 2e-2 of 0 in the oracle are "flip-prone"
+    * maps: rays whose last-sample sigma is within 4e-3 of 0 in the oracle are "flip-prone"
       (alpha_last = [sigma_last > 0], renderer.py:123: a step function) and are excluded and counted;
       of the rest >= 99 % must be within 1e-2 abs on rgb/acc and within 1e-2 * (far-near) on depth,
       and none may exceed 10x that.
@@ -192,7 +192,7 @@ def test_render_rays_fp32_stage_isolated(nb, name, monkeypatch):
 
 
 def bf16_check(out, ref, sigma_last, far_near=4.0):
-    flip = np.abs(sigma_last) < 2e-2
+    flip = np.abs(sigma_last) < 4e-3      # ~5x the measured bf16 error of raw sigma (7e-4)
     keep = ~flip
     res = {"flip_prone": int(flip.sum()), "rays": int(flip.size)}
     for k, scale in (("rgb_map", 1.0), ("acc_map", 1.0), ("depth_map", far_near)):
@@ -358,6 +358,7 @@ def test_train_grads_bf16(nb):
     act = N(v["act"].float())
     xenc = N(v["xenc"].float())[:, :63]
     de = np.repeat(N(v["de"])[:R, :27], S, axis=0)
+    assert np.abs(N(v["de16"].float())[:, :27] - de).max() < 8e-3       # per-sample bf16 copy used by the wgrad
     ins = [xenc] + [act[l - 1] for l in range(1, 5)] + [np.concatenate([xenc, act[4]], 1)] + [act[5], act[6]]
     saved = {"in": ins, "out": bits, "h7": act[7], "hv_in": np.concatenate([act[8], de], 1),
              "hv": N(v["hv"].float()) * hvbits}
