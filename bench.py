@@ -346,7 +346,22 @@ def main():
                 "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + ", burst bf16 matmul",
                 "frac_of_sustained": (achieved / pk["bf16_tflops_sustained"]) if pk.get("bf16_tflops_sustained") else None,
                 "rows_per_launch": rows_max, "flop_per_row": FLOP_PER_ROW_FWD, "avg_launch_ms": avg_ms,
-                "mlp_fwd_share_of_step": mlp_ms_per_step / (sum(ms_steps) / K), "traffic": None}
+                "mlp_fwd_share_of_step": mlp_ms_per_step / (sum(ms_steps) / K)}
+    # DRAM traffic of that launch from the committed ncu --set full captures (profiles/r01_*_ncu_summary.csv):
+    # inference launch of 3 145 728 rows: 22.66 MB read + 3.37 MB written; save-mode launch: 5 396 B/row
+    # (786 432-row capture: 4.211 GB written + 0.032 GB read), scaled to this launch's rows.
+    if args.precision == "bf16":
+        if args.workload == "render" and rows_max == 3145728:
+            roofline["traffic"] = 26.03e6
+            roofline["traffic_source"] = "ncu dram__bytes_read+write, profiles/r01_mlp_fwd_ncu_summary.csv"
+        elif args.workload == "train":
+            roofline["traffic"] = 5396.0 * rows_max
+            roofline["traffic_source"] = ("ncu dram__bytes_read+write per row (save-mode launch, 786 432-row capture, "
+                                          "profiles/r01_train_step_ncu_summary.csv) x rows of this launch")
+        else:
+            roofline["traffic"] = None
+    else:
+        roofline["traffic"] = None
 
     line = {"metric": f"{args.workload}_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload == "train" else "strong",

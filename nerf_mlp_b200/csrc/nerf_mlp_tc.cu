@@ -30,8 +30,9 @@
 namespace nerf {
 using namespace ptx;
 
-constexpr int kThreads = 352;                     // producer, 2 mma issuers, 2 x 4 compute warps
+constexpr int kThreads = 416;                     // producer, 2 mma issuers, 2 x 4 compute warps, 2 store warps
 constexpr int kFirstComputeWarp = 3;
+constexpr int kFirstStoreWarp = 11;               // warp 11 -> tile A, warp 12 -> tile B (save modes only)
 constexpr int kNumGemmsFwd = 10, kNumGemmsBwd = 9;
 
 // ---- shared memory map (bytes) ------------------------------------------------------------------
@@ -45,7 +46,7 @@ constexpr int kOnesBytes = 4096;
 constexpr int kOffHead = kOffOnes + kOnesBytes;              // w_sigma[256] w_rgb[3][128] b_sigma b_rgb[3]
 constexpr int kHeadFloats = 256 + 384 + 4;
 constexpr int kOffBar = kOffHead + ((kHeadFloats * 4 + 127) / 128) * 128;
-constexpr int kNumBars = 2 * kRing + 5;
+constexpr int kNumBars = 2 * kRing + 9;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
@@ -309,6 +310,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   auto bar_act = [&](int t) { return bar0 + 8u * (2 * kRing + t); };       // activations of tile t ready (epilogue -> MMA)
   auto bar_acc = [&](int t) { return bar0 + 8u * (2 * kRing + 2 + t); };   // accumulator of tile t ready (MMA -> epilogue)
   const uint32_t bar_skew = bar0 + 8u * (2 * kRing + 4);                   // one-shot: tile A's issuer is kSkew slots in
+  auto bar_wr = [&](int t) { return bar0 + 8u * (2 * kRing + 5 + t); };    // activation tile t written (epilogue -> store warp)
+  auto bar_cp = [&](int t) { return bar0 + 8u * (2 * kRing + 7 + t); };    // activation tile t copied out (store warp -> epilogue)
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* head = reinterpret_cast<float*>(smem + kOffHead);
   constexpr int kNumGemms = kBwd ? kNumGemmsBwd : kNumGemmsFwd;
@@ -317,10 +320,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
     for (int s = 0; s < kRing; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 2); }
     for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), 128); mbar_init(bar_acc(t), 1); }
     mbar_init(bar_skew, 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_wr(t), 128); mbar_init(bar_cp(t), 1); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(sbase + kOffTmemPtr, 512); tmem_relinquish(); }
-  if (warp >= kFirstComputeWarp) {
+  if (warp >= kFirstComputeWarp && warp < kFirstStoreWarp) {
     const int tid = threadIdx.x - 32 * kFirstComputeWarp;   // 0..255
     // constant A operand of the bias K-step: columns 0,1 = 1, rest 0 (SW32 layout)
     if (tid < 128) {
@@ -401,6 +405,38 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
         }
       }
     }
+  } else if (warp >= kFirstStoreWarp) {
+    // ================= store warps (save modes): copy finished activation tiles to HBM =================
+    // Takes the 64 KB-per-layer tile-image copies off the epilogue warps: wait until the tile is
+    // written, stream it out (shared and HBM images are byte-identical), tell the epilogue warps
+    // that the tile may be overwritten.
+    if constexpr (kBwd || kSave) {
+      const int t = warp - kFirstStoreWarp;
+      const uint8_t* src = smem + kOffAct + t * kActBytes + lane * 16;
+      const int64_t ntiles = a.Mp / kTileM;
+      uint32_t ph = 0;
+      for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
+        const int64_t tile = (int64_t)pair * 2 + t;
+        for (int g = 0; g < 9; ++g) {
+          const int dst_idx = kBwd ? (g == 0 ? 8 : 8 - g) : g;
+          uint8_t* dst = (kBwd ? a.dpre_img : a.act_img) + ((int64_t)dst_idx * ntiles + tile) * 65536 + lane * 16;
+          mbar_wait(bar_wr(t), ph, 1000 + t);
+          ph ^= 1;
+#pragma unroll 1
+          for (int i = 0; i < 128; i += 16) {
+            uint4 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (i + j) * 512);
+            if (i + 16 == 128) {                           // all reads of the tile are done: release it early
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_cp(t));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) *reinterpret_cast<uint4*>(dst + (i + j) * 512) = v[j];
+          }
+        }
+      }
+    }
   } else {
     // ================= prologue + epilogue warps =================
     const int t = (warp - kFirstComputeWarp) >> 2;    // tile A / tile B
@@ -445,7 +481,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
       __syncwarp();     // lanes read each other's rows: nobody may overwrite the tile before all are done
 #endif
     };
-    uint32_t acc_ph = 0;
+    uint32_t acc_ph = 0, cp_ph = 0;
+    bool store_pending = false;                       // an activation-tile copy by the store warp may be in flight
+    auto tile_writable = [&]() {                      // call before overwriting the activation tile
+      if (kStores && store_pending) { mbar_wait(bar_cp(t), cp_ph, 1100 + t); cp_ph ^= 1; store_pending = false; }
+    };
+    auto tile_written = [&]() {                       // writers are proxy-fenced; hand the tile to the store warp
+      if (kStores) { mbar_arrive(bar_wr(t)); store_pending = true; }
+    };
     for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
       const int64_t tile = (int64_t)pair * 2 + t;
       const int64_t row = tile * kTileM + m;
@@ -464,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           acc_ph ^= 1;
           tc_fence_after();
           stores_drained();
+          tile_writable();
           if (g < 9) {
             uint32_t mkw[8];
 #pragma unroll 1
@@ -504,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             fence_proxy_async();
             mbar_arrive(bar_act(t));
             if (kSave) {                                   // off the critical path: the MMAs are already released
-              store_tile(a.act_img + ((int64_t)g * ntiles + tile) * 65536, at_s, 65536);
+              tile_written();
               if (g < 8 && valid) {
                 uint4* mp = reinterpret_cast<uint4*>(a.mask + ((int64_t)g * a.M + row) * 8);
                 mp[0] = make_uint4(mkw[0], mkw[1], mkw[2], mkw[3]);
@@ -582,6 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
         // prologue: d_hv_pre = (d_rgb . W_rgb) * [hv > 0]  (reference autograd of model.py:73-75)
         const float4 dr = valid ? __ldg(reinterpret_cast<const float4*>(a.d_raw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
         stores_drained();
+        tile_writable();
         {
           uint4 mw = valid ? __ldg(reinterpret_cast<const uint4*>(a.hvmask) + row) : make_uint4(0u, 0u, 0u, 0u);
           const uint32_t mws[4] = {mw.x, mw.y, mw.z, mw.w};
@@ -618,6 +663,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           acc_ph ^= 1;
           tc_fence_after();
           stores_drained();
+          tile_writable();
 #pragma unroll 1
           for (int c0 = 0; c0 < 256; c0 += 32) {
             uint32_t r[32];
@@ -643,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           tc_fence_before();
           fence_proxy_async();
           if (g < kNumGemms - 1) mbar_arrive(bar_act(t));
-          store_tile(a.dpre_img + ((int64_t)dst * ntiles + tile) * 65536, at_s, 65536);
+          tile_written();
         }
       }
     }
