@@ -30,7 +30,13 @@
 namespace nerf {
 using namespace ptx;
 
+#ifdef NERF_STORE_WARPS                           // measured: no gain (the copy-out cost is SMEM bandwidth, not issue slots)
+constexpr bool kStoreWarps = true;
 constexpr int kThreads = 416;                     // producer, 2 mma issuers, 2 x 4 compute warps, 2 store warps
+#else
+constexpr bool kStoreWarps = false;
+constexpr int kThreads = 352;                     // producer, 2 mma issuers, 2 x 4 compute warps
+#endif
 constexpr int kFirstComputeWarp = 3;
 constexpr int kFirstStoreWarp = 11;               // warp 11 -> tile A, warp 12 -> tile B (save modes only)
 constexpr int kNumGemmsFwd = 10, kNumGemmsBwd = 9;
@@ -41,11 +47,11 @@ constexpr int kActBytes = 65536;
 constexpr int kOffX = kOffAct + 2 * kActBytes;               // 2 x [128 x 64] bf16, SW128
 constexpr int kXBytes = 16384;
 constexpr int kOffRing = kOffX + 2 * kXBytes;
-constexpr int kOffOnes = kOffRing + kRing * kSlotBytes;      // [128 x 16] bf16, SW32
-constexpr int kOnesBytes = 4096;
+constexpr int kOffOnes = kOffRing + kRing * kSlotBytes;      // [8 x 16] bf16, SW32; all 16 row groups alias it (SBO = 0)
+constexpr int kOnesBytes = 256;
 constexpr int kOffHead = kOffOnes + kOnesBytes;              // w_sigma[256] w_rgb[3][128] b_sigma b_rgb[3]
 constexpr int kHeadFloats = 256 + 384 + 4;
-constexpr int kOffBar = kOffHead + ((kHeadFloats * 4 + 127) / 128) * 128;
+constexpr int kOffBar = kOffHead + kHeadFloats * 4;
 constexpr int kNumBars = 2 * kRing + 9;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   if (warp >= kFirstComputeWarp && warp < kFirstStoreWarp) {
     const int tid = threadIdx.x - 32 * kFirstComputeWarp;   // 0..255
     // constant A operand of the bias K-step: columns 0,1 = 1, rest 0 (SW32 layout)
-    if (tid < 128) {
+    if (tid < 8) {
       const uint32_t one2 = 0x3F803F80u;              // bf16 (1.0, 1.0)
       uint8_t* ones = smem + kOffOnes;
       *reinterpret_cast<uint4*>(ones + sw32_off(tid, 0)) = make_uint4(one2, 0u, 0u, 0u);
@@ -370,6 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
       constexpr uint32_t kHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
       constexpr uint32_t kHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
       constexpr uint32_t kHiSw32 = (256u >> 4) | (1u << 14) | (6u << 29);
+      constexpr uint32_t kHiOnes = (0u >> 4) | (1u << 14) | (6u << 29);      // SBO = 0: every 8-row group reads the same 8 rows
       const uint32_t a_lo_x = ((sbase + kOffX + t * kXBytes) >> 4) | (1u << 16);
       const uint32_t a_lo_act = ((sbase + kOffAct + t * kActBytes) >> 4) | (1u << 16);
       const uint32_t a_lo_ones = ((sbase + kOffOnes) >> 4) | (1u << 16);
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           tc_fence_after();
           const uint32_t kind = fl & 3u;
           const uint32_t a_lo = (kind == A_X ? a_lo_x : (kind == A_ACT ? a_lo_act : a_lo_ones)) + a_add;
-          const uint32_t a_hi = (kind == A_ONES) ? kHiSw32 : kHiSw128;
+          const uint32_t a_hi = (kind == A_ONES) ? kHiOnes : kHiSw128;
           const uint32_t b_lo = b_lo0 + s * (kSlotBytes >> 4);
           const uint32_t b_hi = (fl & kFlagNk2) ? kHiSw64 : kHiSw32;
           const uint32_t idesc = (fl & kFlagN128) ? kIdesc128 : kIdesc256;
@@ -410,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
     // Takes the 64 KB-per-layer tile-image copies off the epilogue warps: wait until the tile is
     // written, stream it out (shared and HBM images are byte-identical), tell the epilogue warps
     // that the tile may be overwritten.
-    if constexpr (kBwd || kSave) {
+    if constexpr ((kBwd || kSave) && kStoreWarps) {
       const int t = warp - kFirstStoreWarp;
       const uint8_t* src = smem + kOffAct + t * kActBytes + lane * 16;
       const int64_t ntiles = a.Mp / kTileM;
@@ -484,10 +491,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
     uint32_t acc_ph = 0, cp_ph = 0;
     bool store_pending = false;                       // an activation-tile copy by the store warp may be in flight
     auto tile_writable = [&]() {                      // call before overwriting the activation tile
-      if (kStores && store_pending) { mbar_wait(bar_cp(t), cp_ph, 1100 + t); cp_ph ^= 1; store_pending = false; }
+      if (kStores && kStoreWarps && store_pending) { mbar_wait(bar_cp(t), cp_ph, 1100 + t); cp_ph ^= 1; store_pending = false; }
     };
-    auto tile_written = [&]() {                       // writers are proxy-fenced; hand the tile to the store warp
-      if (kStores) { mbar_arrive(bar_wr(t)); store_pending = true; }
+    auto tile_written = [&](uint8_t* dst) {           // writers are proxy-fenced; copy the tile image out
+      if (kStores) {
+        if (kStoreWarps) { mbar_arrive(bar_wr(t)); store_pending = true; }
+        else store_tile(dst, at_s, 65536);
+      }
     };
     for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
       const int64_t tile = (int64_t)pair * 2 + t;
@@ -510,22 +520,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           tile_writable();
           if (g < 9) {
             uint32_t mkw[8];
-#pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
-              uint32_t r[32];
-              tmem_ld32(taddr + c0, r);
-              tmem_ld_wait();
+            // one 32-column chunk: sigma head, ReLU mask, convert, swizzled store
+            auto chunk = [&](const uint32_t (&r)[32], int c0) {
               if (g == 7) {                              // sigma head from fp32 post-ReLU activations (model.py:69)
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), head[c0 + j], sigma);
               }
-#ifndef NERF_EXP_NOMASK
               if (kSave) {
                 const uint32_t w = relu_mask32(r);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) if ((c0 >> 5) == i) mkw[i] = w;
               }
-#endif
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 uint4 o;
@@ -543,12 +548,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
                 const int k = c0 + 8 * c;
                 *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
               }
+            };
+#ifdef NERF_EPI_SINGLE
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+              uint32_t r[32];
+              tmem_ld32(taddr + c0, r);
+              tmem_ld_wait();
+              chunk(r, c0);
             }
+#else
+            {                                            // two register buffers: the next chunk's tcgen05.ld is in
+              uint32_t ra[32], rb[32];                   // flight while the current chunk is converted and stored
+              tmem_ld32(taddr, ra);
+#pragma unroll 1
+              for (int c0 = 0; c0 < 256; c0 += 64) {
+                tmem_ld_wait();
+                tmem_ld32(taddr + c0 + 32, rb);
+                chunk(ra, c0);
+                tmem_ld_wait();
+                if (c0 + 64 < 256) tmem_ld32(taddr + c0 + 64, ra);
+                chunk(rb, c0 + 32);
+              }
+            }
+#endif
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_act(t));
             if (kSave) {                                   // off the critical path: the MMAs are already released
-              tile_written();
+              tile_written(a.act_img + ((int64_t)g * ntiles + tile) * 65536);
               if (g < 8 && valid) {
                 uint4* mp = reinterpret_cast<uint4*>(a.mask + ((int64_t)g * a.M + row) * 8);
                 mp[0] = make_uint4(mkw[0], mkw[1], mkw[2], mkw[3]);
@@ -689,7 +717,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           tc_fence_before();
           fence_proxy_async();
           if (g < kNumGemms - 1) mbar_arrive(bar_act(t));
-          tile_written();
+          tile_written(a.dpre_img + ((int64_t)dst * ntiles + tile) * 65536);
         }
       }
     }

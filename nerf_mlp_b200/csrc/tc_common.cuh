@@ -8,7 +8,7 @@
 #define NERF_TC_NK 2          // K-steps (16 wide) per weight slot
 #endif
 #ifndef NERF_TC_RING
-#define NERF_TC_RING 3        // ring slots
+#define NERF_TC_RING 4        // ring slots
 #endif
 #ifndef NERF_TC_SKEW
 #define NERF_TC_SKEW 1        // slots by which tile B's issuer starts behind tile A's
