@@ -23,8 +23,16 @@
 // when both issuers have committed it), which halves the L2->SMEM weight traffic; tile B starts
 // kSkew slots behind tile A so that each tile's epilogue overlaps the other tile's MMAs.
 // TMEM: 2 x 256 fp32 columns (all 512).
+//
+// kCtas = 2 (cta_group::2): two CTAs on the SMs of one TPC form a pair.  Each keeps its own two
+// 128-row tiles and HALF of every weight slot (B is split along N across the pair), so the weight
+// bytes per SM and the B-operand shared-memory reads halve and the ring is twice as deep.  The
+// leader CTA's issuers issue M = 256 MMAs for both CTAs; commits are multicast to both CTAs'
+// barriers; the peer's epilogue threads arrive remotely on the leader's "activations ready"
+// barrier and a relay warp forwards the peer's "slot full" events.
 #include "tc_common.cuh"
 #include <mutex>
+#include <stdlib.h>
 #include <vector>
 
 namespace nerf {
@@ -52,9 +60,9 @@ constexpr int kOnesBytes = 256;
 constexpr int kOffHead = kOffOnes + kOnesBytes;              // w_sigma[256] w_rgb[3][128] b_sigma b_rgb[3]
 constexpr int kHeadFloats = 256 + 384 + 4;
 constexpr int kOffBar = kOffHead + kHeadFloats * 4;
-constexpr int kNumBars = 2 * kRing + 9;
+constexpr int kNumBars = 3 * (2 * kRing) + 5 + (kStoreWarps ? 4 : 0);   // sized for the 2-CTA variant (ring twice as deep)
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
-constexpr int kSmemBytes = kOffTmemPtr + 16;
+constexpr int kSmemBytes = kOffTmemPtr + 8;
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 
 __constant__ Slot c_slots[kMaxSlots];          // forward schedule, then the dgrad schedule
@@ -304,32 +312,43 @@ __device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&r)[32]) {
 }
 
 // kBwd = false: forward (kSave: also write the tensors the backward needs); kBwd = true: dgrad chain
-template <bool kBwd, bool kSave>
+template <bool kBwd, bool kSave, int kCtas>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int kRingK = kRing * kCtas;                 // ring slots per CTA (same bytes, half-size slots in pair mode)
+  constexpr int kSlotK = kSlotBytes / kCtas;            // bytes of a slot held by one CTA
+  const uint32_t rank = (kCtas == 2) ? cluster_ctarank() : 0u;
+  const int unit0 = (kCtas == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work unit of this CTA (pair)
+  const int unit_step = (kCtas == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_units = (kCtas == 2) ? (a.num_pairs + 1) / 2 : a.num_pairs;      // unit = tile pair (1 CTA) / quad (CTA pair)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + kOffBar;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (kRing + s); };
-  auto bar_act = [&](int t) { return bar0 + 8u * (2 * kRing + t); };       // activations of tile t ready (epilogue -> MMA)
-  auto bar_acc = [&](int t) { return bar0 + 8u * (2 * kRing + 2 + t); };   // accumulator of tile t ready (MMA -> epilogue)
-  const uint32_t bar_skew = bar0 + 8u * (2 * kRing + 4);                   // one-shot: tile A's issuer is kSkew slots in
-  auto bar_wr = [&](int t) { return bar0 + 8u * (2 * kRing + 5 + t); };    // activation tile t written (epilogue -> store warp)
-  auto bar_cp = [&](int t) { return bar0 + 8u * (2 * kRing + 7 + t); };    // activation tile t copied out (store warp -> epilogue)
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kRingK + s); };
+  auto bar_pfull = [&](int s) { return bar0 + 8u * (2 * kRingK + s); };    // pair mode, leader: the peer's half of slot s landed
+  constexpr int kB0 = 3 * kRingK;
+  auto bar_act = [&](int t) { return bar0 + 8u * (kB0 + t); };             // activations of tile t ready (epilogue -> MMA)
+  auto bar_acc = [&](int t) { return bar0 + 8u * (kB0 + 2 + t); };         // accumulator of tile t ready (MMA -> epilogue)
+  const uint32_t bar_skew = bar0 + 8u * (kB0 + 4);                         // one-shot: tile A's issuer is kSkew slots in
+  auto bar_wr = [&](int t) { return bar0 + 8u * (kB0 + 5 + t); };          // activation tile t written (epilogue -> store warp)
+  auto bar_cp = [&](int t) { return bar0 + 8u * (kB0 + 7 + t); };          // activation tile t copied out (store warp -> epilogue)
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* head = reinterpret_cast<float*>(smem + kOffHead);
   constexpr int kNumGemms = kBwd ? kNumGemmsBwd : kNumGemmsFwd;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kRing; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 2); }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), 128); mbar_init(bar_acc(t), 1); }
+    for (int s = 0; s < kRingK; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 2); mbar_init(bar_pfull(s), 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), 128 * kCtas); mbar_init(bar_acc(t), 1); }
     mbar_init(bar_skew, 1);
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_wr(t), 128); mbar_init(bar_cp(t), 1); }
+    if (kStoreWarps) for (int t = 0; t < 2; ++t) { mbar_init(bar_wr(t), 128); mbar_init(bar_cp(t), 1); }
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(sbase + kOffTmemPtr, 512); tmem_relinquish(); }
+  if (warp == 1) {
+    if (kCtas == 2) { tmem_alloc2(sbase + kOffTmemPtr, 512); tmem_relinquish2(); }
+    else { tmem_alloc(sbase + kOffTmemPtr, 512); tmem_relinquish(); }
+  }
   if (warp >= kFirstComputeWarp && warp < kFirstStoreWarp) {
     const int tid = threadIdx.x - 32 * kFirstComputeWarp;   // 0..255
     // constant A operand of the bias K-step: columns 0,1 = 1, rest 0 (SW32 layout)
@@ -348,6 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  if (kCtas == 2) cluster_sync();                     // both CTAs' barriers exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int slot0 = kBwd ? c_nslots_fwd : 0;
@@ -357,20 +377,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
     // ================= weight producer =================
     if (lane == 0) {
       uint32_t g = 0;
-      for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
         for (int i = 0; i < nslots; ++i, ++g) {
-          const uint32_t s = g % kRing, ph = (g / kRing) & 1;
+          const uint32_t s = g % kRingK, ph = (g / kRingK) & 1;
           const uint2 rec = *reinterpret_cast<const uint2*>(&c_slots[slot0 + i]);      // goff, bytes
+          const uint32_t bytes = rec.y / kCtas;          // pair mode: this CTA's N-half of the slot
           mbar_wait(bar_empty(s), ph ^ 1, 100 + (int)s);
-          mbar_expect_tx(bar_full(s), rec.y);
-          bulk_g2s(sbase + kOffRing + s * kSlotBytes, a.packed + rec.x, rec.y, bar_full(s));
+          mbar_expect_tx(bar_full(s), bytes);
+          bulk_g2s(sbase + kOffRing + s * kSlotK, a.packed + rec.x + rank * bytes, bytes, bar_full(s));
         }
       }
     }
   } else if (warp < kFirstComputeWarp) {
     // ================= MMA issuers: warp 1 -> tile A, warp 2 -> tile B =================
     // The whole warp walks the schedule (uniform control flow); one elected lane issues.
-    {
+    if (kCtas == 2 && rank != 0) {
+      // peer CTA of a pair: its issuer warps do not issue; warp 1 relays "my half of slot s landed"
+      // to the leader, whose MMAs read both halves.
+      if (warp == 1) {
+        uint32_t s = 0, ph = 0;
+        for (int unit = unit0; unit < num_units; unit += unit_step) {
+          for (int i = 0; i < nslots; ++i) {
+            mbar_wait(bar_full(s), ph, 250 + (int)s);
+            if (lane == 0) mbar_arrive_cluster(mapa(bar_pfull(s), 0));
+            __syncwarp();
+            if (++s == kRingK) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    } else {
       const int t = warp - 1;
       // descriptor words that never change: hi = SBO | version | layout, lo = (addr >> 4) | LBO
       constexpr uint32_t kHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -382,33 +417,45 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
       const uint32_t a_lo_ones = ((sbase + kOffOnes) >> 4) | (1u << 16);
       const uint32_t b_lo0 = ((sbase + kOffRing) >> 4) | (1u << 16);
       const uint32_t d_tmem = tmem_base + (uint32_t)t * 256;
-      constexpr uint32_t kIdesc256 = make_idesc_bf16(kTileM, 256), kIdesc128 = make_idesc_bf16(kTileM, 128);
+      constexpr uint32_t kIdesc256 = make_idesc_bf16(kTileM * kCtas, 256), kIdesc128 = make_idesc_bf16(kTileM * kCtas, 128);
       uint32_t s = 0, ph = 0, act_ph = 0;
       if (t == 1) mbar_wait(bar_skew, 0, 500);            // one-shot start offset behind tile A
-      for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
         for (int i = 0; i < nslots; ++i) {
           const uint4 rec = *reinterpret_cast<const uint4*>(&c_slots[slot0 + i]);
           const uint32_t a_add = rec.z, fl = rec.w;
           mbar_wait(bar_full(s), ph, 200 + (int)s);
+          // plain (cta-scope) waits, as CUTLASS's 2-SM pipelines do: the remote arrivals are
+          // release.cluster and the data they publish is consumed by the async proxy (the MMA)
+          if (kCtas == 2) mbar_wait(bar_pfull(s), ph, 220 + (int)s);
           if (fl & kFlagFirst) { mbar_wait(bar_act(t), act_ph, 300 + t); act_ph ^= 1; }
           tc_fence_after();
           const uint32_t kind = fl & 3u;
           const uint32_t a_lo = (kind == A_X ? a_lo_x : (kind == A_ACT ? a_lo_act : a_lo_ones)) + a_add;
           const uint32_t a_hi = (kind == A_ONES) ? kHiOnes : kHiSw128;
-          const uint32_t b_lo = b_lo0 + s * (kSlotBytes >> 4);
+          const uint32_t b_lo = b_lo0 + s * (kSlotK >> 4);
           const uint32_t b_hi = (fl & kFlagNk2) ? kHiSw64 : kHiSw32;
           const uint32_t idesc = (fl & kFlagN128) ? kIdesc128 : kIdesc256;
           if (elect_one()) {
-            mma_bf16_ss(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
-                        (fl & kFlagFirst) ? 0u : 1u);
-            if (fl & kFlagNk2)
-              mma_bf16_ss(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2), ((uint64_t)b_hi << 32) | (b_lo + 2), idesc, 1u);
-            tc_commit(bar_empty(s));                      // slot is free once both issuers' MMAs on it retired
-            if (fl & kFlagLast) tc_commit(bar_acc(t));
-            if (t == 0 && i == kSkew - 1 && pair == (int)blockIdx.x) mbar_arrive(bar_skew);
+            if (kCtas == 2) {
+              mma_bf16_ss_2cta(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
+                               (fl & kFlagFirst) ? 0u : 1u);
+              if (fl & kFlagNk2)
+                mma_bf16_ss_2cta(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2), ((uint64_t)b_hi << 32) | (b_lo + 2), idesc, 1u);
+              tc_commit_mc2(bar_empty(s), 3);               // both CTAs' producers may refill the slot
+              if (fl & kFlagLast) tc_commit_mc2(bar_acc(t), 3);   // both CTAs' epilogues may read their accumulators
+            } else {
+              mma_bf16_ss(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
+                          (fl & kFlagFirst) ? 0u : 1u);
+              if (fl & kFlagNk2)
+                mma_bf16_ss(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2), ((uint64_t)b_hi << 32) | (b_lo + 2), idesc, 1u);
+              tc_commit(bar_empty(s));                      // slot is free once both issuers' MMAs on it retired
+              if (fl & kFlagLast) tc_commit(bar_acc(t));
+            }
+            if (t == 0 && i == kSkew - 1 && unit == unit0) mbar_arrive(bar_skew);
           }
           __syncwarp();
-          if (++s == kRing) { s = 0; ph ^= 1; }
+          if (++s == kRingK) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -422,8 +469,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
       const uint8_t* src = smem + kOffAct + t * kActBytes + lane * 16;
       const int64_t ntiles = a.Mp / kTileM;
       uint32_t ph = 0;
-      for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
-        const int64_t tile = (int64_t)pair * 2 + t;
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        const int64_t tile = ((int64_t)unit * kCtas + rank) * 2 + t;
         for (int g = 0; g < 9; ++g) {
           const int dst_idx = kBwd ? (g == 0 ? 8 : 8 - g) : g;
           uint8_t* dst = (kBwd ? a.dpre_img : a.act_img) + ((int64_t)dst_idx * ntiles + tile) * 65536 + lane * 16;
@@ -499,8 +546,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
         else store_tile(dst, at_s, 65536);
       }
     };
-    for (int pair = blockIdx.x; pair < a.num_pairs; pair += gridDim.x) {
-      const int64_t tile = (int64_t)pair * 2 + t;
+    // "activations of tile t ready": local arrive, or (peer CTA of a pair) remote arrive at the leader
+    const uint32_t act_remote = (kCtas == 2 && rank != 0) ? mapa(bar_act(t), 0) : 0u;
+    auto act_arrive = [&]() {
+      if (kCtas == 2 && rank != 0) mbar_arrive_cluster(act_remote); else mbar_arrive(bar_act(t));
+    };
+    for (int unit = unit0; unit < num_units; unit += unit_step) {
+      const int64_t tile = ((int64_t)unit * kCtas + rank) * 2 + t;
       const int64_t row = tile * kTileM + m;
       const bool valid = row < a.M;
       const int64_t ntiles = a.Mp / kTileM;
@@ -509,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
         stores_drained();
         fwd_prologue(a, row, m, xt);
         fence_proxy_async();
-        mbar_arrive(bar_act(t));
+        act_arrive();
         if (kSave) store_tile(a.xenc_img + tile * 16384, xt_s, 16384);
         float sigma = head[640];
         for (int g = 0; g < kNumGemms; ++g) {
@@ -574,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 #endif
             tc_fence_before();
             fence_proxy_async();
-            mbar_arrive(bar_act(t));
+            act_arrive();
             if (kSave) {                                   // off the critical path: the MMAs are already released
               tile_written(a.act_img + ((int64_t)g * ntiles + tile) * 65536);
               if (g < 8 && valid) {
@@ -675,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           }
         }
         fence_proxy_async();
-        mbar_arrive(bar_act(t));
+        act_arrive();
         store_tile(a.dhv_img + tile * 32768, at_s, 32768);
         for (int g = 0; g < kNumGemms; ++g) {
           // g = 0: d_bott (no mask) | g = 1: d_h7 (+ sigma term, mask 7) | g >= 2: d_pre_{8-g} (mask 8-g)
@@ -716,7 +768,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           }
           tc_fence_before();
           fence_proxy_async();
-          if (g < kNumGemms - 1) mbar_arrive(bar_act(t));
+          if (g < kNumGemms - 1) act_arrive();
           tile_written(a.dpre_img + ((int64_t)dst * ntiles + tile) * 65536);
         }
       }
@@ -726,14 +778,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 #endif
   }
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (kCtas == 2) cluster_sync();                     // the peer may still be signalling this CTA's barriers
+  if (warp == 1) {
+    if (kCtas == 2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 size_t mlp_tc_workspace_bytes(int64_t M, int save) { return ws_layout(M, save).total; }
 
 static int sm_count_cached = 0;
-template <bool kBwd, bool kSave>
-static int launch_tc(const TcArgs& a, cudaStream_t st) {
+static int num_ctas() {         // NERF_TC_CTAS_RT=1|2 overrides the compiled default (kernel-variant sweeps)
+  static int n = [] {
+    const char* e = getenv("NERF_TC_CTAS_RT");
+    const int v = e ? atoi(e) : kCtasDefault;
+    return v == 2 ? 2 : 1;
+  }();
+  return n;
+}
+template <bool kBwd, bool kSave, int kCtas>
+static int launch_tc_impl(const TcArgs& a, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     int dev = 0;
@@ -742,13 +805,29 @@ static int launch_tc(const TcArgs& a, cudaStream_t st) {
     NERF_CUDA(cudaGetDeviceProperties(&p, dev));
     NERF_CHECK_ARG(p.major == 10, "libnerf_b200 needs an sm_100 device (found sm_%d%d); there is no fallback", p.major, p.minor);
     sm_count_cached = p.multiProcessorCount;
-    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<kBwd, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<kBwd, kSave, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done = true;
   }
-  const int grid = a.num_pairs < sm_count_cached ? a.num_pairs : sm_count_cached;
-  mlp_tc_kernel<kBwd, kSave><<<grid, kThreads, kSmemBytes, st>>>(a);
+  const int units = (kCtas == 2) ? (a.num_pairs + 1) / 2 : a.num_pairs;
+  const int max_units = sm_count_cached / kCtas;
+  const int grid = (units < max_units ? units : max_units) * kCtas;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (kCtas == 2) ? 1 : 0;
+  NERF_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<kBwd, kSave, kCtas>, a));
   NERF_LAUNCH_CHECK(kBwd ? "mlp_tc_kernel<dgrad>" : "mlp_tc_kernel<fwd>");
   return 0;
+}
+template <bool kBwd, bool kSave>
+static int launch_tc(const TcArgs& a, cudaStream_t st) {
+  return num_ctas() == 2 ? launch_tc_impl<kBwd, kSave, 2>(a, st) : launch_tc_impl<kBwd, kSave, 1>(a, st);
 }
 
 static void fill_saved(TcArgs& a, void* ws, const WsLayout& L) {

@@ -20,9 +20,13 @@ constexpr int kNK = NERF_TC_NK;
 constexpr int kRing = NERF_TC_RING;
 constexpr int kSkew = NERF_TC_SKEW;
 static_assert(kNK == 1 || kNK == 2, "slot = 1 or 2 K-steps");
-static_assert(kSkew >= 1 && kSkew + 1 < kRing, "ring must hold the skew plus at least one prefetch slot");
+static_assert(kSkew >= 1 && kSkew + 1 < 2 * kRing, "ring must hold the skew plus at least one prefetch slot");
 constexpr int kSlotBytes = 8192 * kNK;            // 256 rows x 32 B x NK
 constexpr int kTileM = 128;
+#ifndef NERF_TC_CTAS
+#define NERF_TC_CTAS 1        // 2 = CTA pairs (cta_group::2): B operand split across two SMs
+#endif
+constexpr int kCtasDefault = NERF_TC_CTAS;
 
 // ---- swizzled K-major element offsets (bytes): 16-byte chunk index XOR row bits, as applied by
 // TMA / UMMA for SWIZZLE_{32,64,128}B ------------------------------------------------------------
@@ -66,7 +70,7 @@ constexpr int kMaxSlots = 192;
 //           de16  img  [Mp x 64]     encoded view direction per sample (27 used)          (save only)
 //           mask  u32  [8][M][8]     ReLU masks of h0..h7; hvmask u32 [M][4]   (row-major, save only)
 // backward: dpre  img  [9][Mp x 256] d(pre-activation) of layers 0..7, d(bottleneck); dhv img [Mp x 128];
-//           draw16 img [Mp x 64]     d_raw as bf16 (4 used)   -- Mp = rows padded to whole tile pairs
+//           draw16 img [Mp x 64]     d_raw as bf16 (4 used)   -- Mp = rows padded to a multiple of 512
 struct WsLayout {
   size_t vb, de, act, hv, xenc, de16, mask, hvmask, dpre, dhv, total;
   int64_t Mp;
@@ -75,7 +79,7 @@ inline WsLayout ws_layout(int64_t M, int save) {
   WsLayout w{};
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) & ~(size_t)1023; return r; };
-  w.Mp = (M + 2 * kTileM - 1) / (2 * kTileM) * (2 * kTileM);
+  w.Mp = (M + 4 * kTileM - 1) / (4 * kTileM) * (4 * kTileM);      // whole tile pairs per CTA, whole quads per CTA pair
   w.vb = take((size_t)M * 128 * 4);
   if (save) {
     w.de = take((size_t)M * 32 * 4);

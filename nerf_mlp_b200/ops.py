@@ -183,7 +183,7 @@ def bf16_workspace_views(ws, M):
     backward (layout: csrc/tc_common.cuh ws_layout).  For tests and debugging."""
     def al(n):
         return (n + 1023) & ~1023
-    Mp = (M + 255) // 256 * 256
+    Mp = (M + 511) // 512 * 512
     out, off = {}, 0
     spec = (("vb", M * 128 * 4, torch.float32, (M, 128), None),
             ("de", M * 32 * 4, torch.float32, (M, 32), None),
