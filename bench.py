@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (train) / total rays (render)")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="train: enqueue the step eagerly instead of replaying the CUDA graph")
+    ap.add_argument("--autograd", action="store_true", help="train: the reference's loop on the drop-in classes (autograd + FlatAdam)")
     return ap.parse_args()
 
 
@@ -246,7 +248,7 @@ def main():
         renderer = nb.NeRFRenderer(model, dev, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=1.0)
         opt = nb.FlatAdam(model, lr=5e-4)
 
-        def step(o_, d_, tgt_):
+        def step_autograd(o_, d_, tgt_):
             out = renderer._render_rays(o_, d_)
             loss = ops.mse_loss(out["rgb_map"], tgt_)               # scripts/train.py:376
             opt.zero_grad()
@@ -256,12 +258,22 @@ def main():
 
         units_per_step = rays * world
         flop_per_unit = (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) * FLOP_PER_ROW_FWD + (N_SAMPLES + N_IMPORTANCE) * FLOP_PER_ROW_BWD
-        run = lambda: step(o, d, tgt)
         ho, hd, ht = (torch.from_numpy(a).pin_memory() for a in (o_np, d_np, tgt_np))
+        if args.autograd:
+            train_step = None
+            run = lambda: step_autograd(o, d, tgt)
 
-        def run_e2e():
-            o_ = ho.to(dev, non_blocking=True); d_ = hd.to(dev, non_blocking=True); t_ = ht.to(dev, non_blocking=True)
-            return float(step(o_, d_, t_))                          # loss read back: D2H + sync every step
+            def run_e2e():
+                o_ = ho.to(dev, non_blocking=True); d_ = hd.to(dev, non_blocking=True); t_ = ht.to(dev, non_blocking=True)
+                return float(step_autograd(o_, d_, t_).detach())    # loss read back: D2H + sync every step
+        else:
+            # the public training API: one CUDA-graph replay per step (nerf_mlp_b200.TrainStep)
+            train_step = nb.TrainStep(renderer, opt, rays, graph=not args.no_graph, stage_events=True)
+            train_step.load_batch(o, d, tgt)                        # inputs resident in HBM for `value`
+            run = lambda: train_step()
+
+            def run_e2e():
+                return float(train_step(ho, hd, ht))                # H2D of the batch + replay + loss read back (sync)
         h2d, d2h = 3 * rays * 12, 4
     else:
         total = args.rays or 640000
@@ -300,6 +312,7 @@ def main():
     launches0 = dll.nerf_launch_count()
     timed_fwd.on = True
     evs = []
+    stage_acc = {} if (args.workload == "train" and train_step is not None) else None
     barrier()
     wall0 = time.perf_counter()
     for _ in range(K):
@@ -309,10 +322,16 @@ def main():
         run()
         e1.record()
         evs.append((e0, e1))
+        if stage_acc is not None:                                    # per-stage device times of THIS step (events inside the graph)
+            e1.synchronize()
+            for k_, v_ in train_step.stage_times().items():
+                stage_acc[k_] = stage_acc.get(k_, 0.0) + v_
     barrier()
     wall = time.perf_counter() - wall0
     timed_fwd.on = False
     launches = dll.nerf_launch_count() - launches0
+    if stage_acc is not None and train_step.use_graph:
+        launches = K * train_step.launches_per_step                 # replayed launches are not seen by the host-side counter
     clocks = sampler.stop()
     ms_steps = [a.elapsed_time(b) for a, b in evs]
     ms_total = torch.tensor([sum(ms_steps)], device=dev, dtype=torch.float64)
@@ -336,11 +355,16 @@ def main():
 
     # --- roofline of the dominant kernel: fused MLP forward (largest launch = fine pass) --------------
     pk = peaks()
-    rows_max = max(n for n, _, _ in mlp_events)
-    fine = [(n, a.elapsed_time(b)) for n, a, b in mlp_events if n == rows_max]
-    avg_ms = sum(ms for _, ms in fine) / len(fine)
+    if stage_acc is not None:
+        rows_max = rays * (N_SAMPLES + N_IMPORTANCE)
+        avg_ms = stage_acc["mlp_fwd_fine_save"] / K
+        mlp_ms_per_step = (stage_acc["mlp_fwd_fine_save"] + stage_acc["mlp_fwd_coarse"]) / K
+    else:
+        rows_max = max(n for n, _, _ in mlp_events)
+        fine = [(n, a.elapsed_time(b)) for n, a, b in mlp_events if n == rows_max]
+        avg_ms = sum(ms for _, ms in fine) / len(fine)
+        mlp_ms_per_step = sum(a.elapsed_time(b) for _, a, b in mlp_events) / K
     achieved = rows_max * FLOP_PER_ROW_FWD / (avg_ms * 1e-3) / 1e12
-    mlp_ms_per_step = sum(a.elapsed_time(b) for _, a, b in mlp_events) / K
     roofline = {"kernel": "mlp_fwd_tc_kernel (fused PE + 8x256 MLP + heads), fine pass" if args.precision == "bf16" else "fp32 check-mode SGEMM chain",
                 "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + ", burst bf16 matmul",
@@ -371,6 +395,11 @@ def main():
             "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roofline}
 
+    if stage_acc is not None:
+        line["stage_ms"] = {k_: round(v_ / K, 5) for k_, v_ in stage_acc.items()}
+        line["config"]["step_api"] = "nerf_mlp_b200.TrainStep (" + ("CUDA graph replay" if train_step.use_graph else "eager launches") + ")"
+    elif args.workload == "train":
+        line["config"]["step_api"] = "NeRFRenderer._render_rays + loss.backward() + FlatAdam.step (autograd)"
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         rays_cpu = 256 if args.workload == "train" else 512
         sec = time_cpu(args.workload, rays_cpu, 3, 1)

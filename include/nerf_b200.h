@@ -128,6 +128,22 @@ int nerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
 int nerf_mse_loss(const float* pred, const float* target, int64_t n, float* loss, float* d_pred,
                   void* stream);
 
+/* ---- training-step glue kept on the device ------------------------------
+ * The reference reads loss / PSNR / gradient norm back every step (scripts/train.py:376-390:
+ * loss.item(), calculate_psnr -> .cpu().numpy() :33-37, get_gradient_norm -> 24x .item() :60-67)
+ * and computes the Adam scalars in Python (torch/optim/adam.py).  These two entry points keep all
+ * of that in a device-resident state block of NERF_TRAIN_STATE_DOUBLES doubles, so that one
+ * training step is a fixed launch sequence (capturable as a CUDA graph) with no host sync:
+ *   state[0..5]  = lr, beta1, beta2, eps, grad_scale, step      (written by the host; step 0-based)
+ *   state[10..12] = loss, psnr (10 log10(1/loss), data_range 1), grad_norm (|grad_scale * g|_2)
+ * nerf_train_prepare: step += 1, derives that step's Adam scalars, fills the metrics
+ *   (loss nullable -> metrics 0/inf);  deterministic (block-ordered fp64 reduction).
+ * nerf_adam_step_dev: nerf_adam_step with every scalar read from the prepared state block. */
+#define NERF_TRAIN_STATE_DOUBLES 96
+int nerf_train_prepare(double* state, const float* loss, const float* flat_grads, int64_t n, void* stream);
+int nerf_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const double* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,8 @@ The dataset loader (nerfmlp/data.py) is host-side I/O outside the hot path and i
 from .model import NeRFMLP, PositionalEncoding
 from .renderer import NeRFRenderer
 from .optim import FlatAdam
+from .train import TrainStep
 from . import dist
 
 __version__ = "1.0.0"
-__all__ = ["NeRFMLP", "NeRFRenderer", "PositionalEncoding", "FlatAdam", "dist"]
+__all__ = ["NeRFMLP", "NeRFRenderer", "PositionalEncoding", "FlatAdam", "TrainStep", "dist"]

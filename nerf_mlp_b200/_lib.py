@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("NERF_B200_LIB") or os.path.join(_HERE, "csrc", "libne
 
 N_PARAMS = 595844
 PREC_BF16, PREC_FP32 = 0, 1
+TRAIN_STATE_DOUBLES = 96
 
 _P = c_void_p
 # name -> (restype, argtypes); mirrors include/nerf_b200.h line by line
@@ -39,6 +40,8 @@ SIGNATURES = {
     "nerf_resample_merge": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "nerf_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, c_float, _P]),
     "nerf_mse_loss": (c_int, [_P, _P, c_int64, _P, _P, _P]),
+    "nerf_train_prepare": (c_int, [_P, _P, _P, c_int64, _P]),
+    "nerf_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
 }
 
 _dll = None

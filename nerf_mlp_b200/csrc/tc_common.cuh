@@ -24,7 +24,7 @@ static_assert(kSkew >= 1 && kSkew + 1 < 2 * kRing, "ring must hold the skew plus
 constexpr int kSlotBytes = 8192 * kNK;            // 256 rows x 32 B x NK
 constexpr int kTileM = 128;
 #ifndef NERF_TC_CTAS
-#define NERF_TC_CTAS 1        // 2 = CTA pairs (cta_group::2): B operand split across two SMs
+#define NERF_TC_CTAS 2        // 2 = CTA pairs (cta_group::2): B operand split across two SMs
 #endif
 constexpr int kCtasDefault = NERF_TC_CTAS;
 

@@ -1,0 +1,284 @@
+"""One optimisation step of the reference's training loop, kept entirely on the device
+(SURVEY.md section 8f row 1).
+
+The reference's loop body (scripts/train.py:368-388)
+
+    rgb_pred = renderer._render_rays(ray_o, ray_d)['rgb_map']          # :374
+    loss = torch.mean((rgb_pred - target_rgb) ** 2)                    # :376
+    batch_psnr = calculate_psnr(rgb_pred, target_rgb)                  # :379  (.cpu().numpy() -> skimage)
+    optimizer.zero_grad(); loss.backward()                             # :381-382
+    grad_norm = get_gradient_norm(model)                               # :385  (24x .item())
+    optimizer.step(); scheduler.step()                                 # :387-388
+
+runs here as a fixed sequence of libnerf_b200 launches with no autograd graph and no host sync:
+loss, PSNR and the gradient norm are device scalars (``TrainStep.metrics``), the Adam step counter
+and learning rate live in a device state block, and the whole sequence is captured ONCE as a CUDA
+graph and replayed (``graph=True``), which removes the ~25 Python/ctypes launches per step that
+otherwise dominate a 1024-ray step.  With ``graph=False`` the same sequence is enqueued eagerly
+(used by the tests to show graph replay == eager, and == the autograd path of ops.RenderPassFn).
+
+Data-parallel (world_size > 1): the step is two graphs with ONE flat NCCL all-reduce between them
+(the only exchange step of the path).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib, ops
+from ._lib import check, dll, ptr, stream_ptr
+
+_ST_LR, _ST_B1, _ST_B2, _ST_EPS, _ST_SCALE, _ST_STEP = range(6)
+_ST_LOSS, _ST_PSNR, _ST_GNORM = 10, 11, 12
+
+
+class TrainStep:
+    """``step = TrainStep(renderer, optimizer, n_rays); loss = step(rays_o, rays_d, target)``.
+
+    * ``renderer``  -- nerf_mlp_b200.NeRFRenderer (its knobs are read at construction/capture time;
+      call :meth:`recapture` after changing them)
+    * ``optimizer`` -- nerf_mlp_b200.FlatAdam on the same model; LR schedulers attached to it keep
+      working: the current ``param_groups[0]['lr']`` is pushed to the device whenever it changes
+    * ``n_rays``    -- fixed batch size (the graph is shape-static, like the reference's DataLoader
+      with a fixed batch_size)
+
+    Returns the loss as a 0-d device tensor (no sync).  ``metrics`` -> device tensor
+    ``[loss, psnr, grad_norm]`` (float64), ``read_metrics()`` -> the same three as Python floats
+    (one D2H copy + sync, for the periodic logging the reference does every step).
+    """
+
+    def __init__(self, renderer, optimizer, n_rays, *, graph=True, warmup=2, stage_events=False):
+        self.renderer, self.opt, self.model = renderer, optimizer, renderer.model
+        if torch.device(renderer.device).type != "cuda":
+            raise RuntimeError("nerf_mlp_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if optimizer.model is not self.model:
+            raise ValueError("TrainStep: optimizer and renderer must share one NeRFMLP")
+        if renderer.N_importance <= 0:
+            raise NotImplementedError("TrainStep implements the coarse+fine step (N_importance > 0)")
+        if renderer.coarse_grad:
+            raise NotImplementedError("TrainStep implements the reference's loss (fine rgb_map only, "
+                                      "scripts/train.py:374-376); coarse_grad=True needs the autograd path")
+        self.R = int(n_rays)
+        self.dev = renderer.device
+        m = self.model
+        m._ensure_flat()
+        m._bind_flat_grads()
+        if optimizer._m is None or optimizer._m.device != m.flat_params.device:
+            optimizer._m = torch.zeros_like(m.flat_params)
+            optimizer._v = torch.zeros_like(m.flat_params)
+        f32 = dict(device=self.dev, dtype=torch.float32)
+        self.rays_o = torch.zeros((self.R, 3), **f32)
+        self.rays_d = torch.zeros((self.R, 3), **f32)
+        self.rays_d[:, 2] = -1.0
+        self.target = torch.zeros((self.R, 3), **f32)
+        self.state = torch.zeros(_lib.TRAIN_STATE_DOUBLES, device=self.dev, dtype=torch.float64)
+        self._loss = torch.zeros((), **f32)
+        self._lr_pushed = None
+        self._step_pushed = None
+        self.use_graph = bool(graph)
+        self._graphs = None
+        self._keep = None
+        self._warmup = int(warmup)
+        self._ptrs = None
+        # optional device timeline: one (external, graph-capturable) CUDA event after every stage
+        self.stage_events = bool(stage_events)
+        self._marks = []
+        self._push_state(force=True)
+        if self.use_graph:
+            self.recapture()
+
+    # ---- device state block ----------------------------------------------------------------------
+    def _world(self):
+        return self.opt._world_size()
+
+    def _push_state(self, force=False):
+        g = self.opt.param_groups[0]
+        lr = float(g["lr"])
+        if force or self._step_pushed != self.opt._step:
+            vals = [lr, float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), 1.0 / self._world(),
+                    float(self.opt._step)]
+            self.state[:6].copy_(torch.tensor(vals, dtype=torch.float64))
+            self._lr_pushed, self._step_pushed = lr, self.opt._step
+        elif lr != self._lr_pushed:
+            self.state[_ST_LR:_ST_LR + 1].copy_(torch.tensor([lr], dtype=torch.float64))
+            self._lr_pushed = lr
+
+    # ---- the launch sequence -----------------------------------------------------------------------
+    def _mark(self, name):
+        if self.stage_events:
+            # inside a capture the record must be an "external" event node (and only there)
+            e = torch.cuda.Event(enable_timing=True, external=torch.cuda.is_current_stream_capturing())
+            e.record(torch.cuda.current_stream(self.dev))
+            self._marks.append((name, e))
+
+    def stage_times(self):
+        """{stage: ms} of the last step (device time between consecutive stage events; needs
+        stage_events=True and a synchronize by the caller)."""
+        out = {}
+        for (_, e0), (name, e1) in zip(self._marks[:-1], self._marks[1:]):
+            if name != "start":
+                out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
+    def _fwd_bwd(self):
+        """render (coarse no-save, resample, fine save) -> MSE -> analytic backward into the flat
+        gradient buffer.  RNG draws in the reference's order (renderer.py:60, :136, :182, :136)."""
+        r, m, R = self.renderer, self.model, self.R
+        prec = r._prec()
+        o, d = self.rays_o, self.rays_d
+        white, cs = bool(r.white_bkgd), float(r.coord_scale)
+        self._mark("start")
+        t_rand = torch.rand((R, r.N_samples), device=self.dev) if r.perturb > 0 else None
+        z = ops.stratified_z(r._linspace(r.N_samples), t_rand, R, r.near, r.far)
+        noise0 = (torch.randn(z.shape, device=self.dev) * r.raw_noise_std).contiguous() if r.raw_noise_std > 0. else None
+        self._mark("stratified_z")
+        raw0, _ = ops.mlp_fwd_rays(m, o, d, z, cs, prec, False)
+        self._mark("mlp_fwd_coarse")
+        rgb0, depth0, acc0, w0 = ops.composite_fwd(raw0, z, d, noise0, white, True)
+        self._mark("composite_fwd_coarse")
+        u = r._linspace(r.N_importance) if r.perturb == 0. else torch.rand((R, r.N_importance), device=self.dev)
+        z_fine = ops.resample_merge(z, w0, u)
+        noise1 = (torch.randn(z_fine.shape, device=self.dev) * r.raw_noise_std).contiguous() if r.raw_noise_std > 0. else None
+        self._mark("resample_merge")
+        raw1, ws = ops.mlp_fwd_rays(m, o, d, z_fine, cs, prec, True)
+        self._mark("mlp_fwd_fine_save")
+        rgb, depth, acc, _ = ops.composite_fwd(raw1, z_fine, d, noise1, white, False)
+        d_rgb = torch.empty_like(rgb)
+        check(dll().nerf_mse_loss(ptr(rgb), ptr(self.target), rgb.numel(), ptr(self._loss), ptr(d_rgb),
+                                  stream_ptr(self.dev)), "nerf_mse_loss")
+        d_raw = ops.composite_bwd(raw1, z_fine, d, noise1, white, d_rgb)
+        m._flat_grad.zero_()                                                 # optimizer.zero_grad()
+        self._mark("composite_fwd_fine+mse+composite_bwd")
+        ops.mlp_bwd(m, d_raw, ws, prec, m._flat_grad, z_fine.shape[1])
+        self._mark("mlp_bwd(dgrad+wgrad)")
+        self.outputs = {"rgb_map": rgb, "depth_map": depth, "acc_map": acc,
+                        "rgb_map_coarse": rgb0, "depth_map_coarse": depth0, "acc_map_coarse": acc0}
+        return (t_rand, z, noise0, raw0, w0, u, z_fine, noise1, raw1, ws, d_rgb, d_raw)
+
+    def _update(self):
+        """metrics + Adam (device-side scalars) + bf16 weight re-pack."""
+        m, opt = self.model, self.opt
+        n = m.flat_params.numel()
+        st = stream_ptr(self.dev)
+        if self._world() > 1:
+            self._mark("grad_allreduce")
+        check(dll().nerf_train_prepare(ptr(self.state), ptr(self._loss), ptr(m._flat_grad), n, st), "nerf_train_prepare")
+        check(dll().nerf_adam_step_dev(ptr(m.flat_params), ptr(m._flat_grad), ptr(opt._m), ptr(opt._v), n,
+                                       ptr(self.state), st), "nerf_adam_step_dev")
+        if r_is_bf16(self.renderer):
+            check(dll().nerf_pack_weights(ptr(m.flat_params), ptr(m._packed), st), "nerf_pack_weights")
+        self._mark("metrics+adam+repack")
+
+    def _allreduce(self):
+        if self._world() > 1:
+            torch.distributed.all_reduce(self.model._flat_grad, op=torch.distributed.ReduceOp.SUM,
+                                         group=self.opt.process_group)
+
+    def _eager(self):
+        self._marks = []
+        keep = self._fwd_bwd()
+        self._allreduce()
+        self._update()
+        return keep
+
+    # ---- capture -------------------------------------------------------------------------------------
+    def _live_ptrs(self):
+        m, opt = self.model, self.opt
+        m._ensure_flat()
+        m._bind_flat_grads()
+        return (m.flat_params.data_ptr(), m._flat_grad.data_ptr(), opt._m.data_ptr(), opt._v.data_ptr(),
+                m._packed.data_ptr() if m._packed is not None else 0)
+
+    def recapture(self):
+        """(Re)capture the step.  Warm-up steps run eagerly on a side stream first (lazy library
+        initialisation, allocator warm-up); parameters, Adam moments and the RNG state are restored
+        afterwards, so constructing a TrainStep does not train."""
+        m, opt = self.model, self.opt
+        if r_is_bf16(self.renderer):
+            m.packed_weights()                                        # clean packed image before capture
+        snap = (m.flat_params.clone(), opt._m.clone(), opt._v.clone(), self.state.clone())
+        rng = torch.cuda.get_rng_state(self.dev)
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(self._warmup):
+                self._eager()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self._graphs, self._keep, self._marks = [], [], []
+        pool = None
+        launches0 = dll().nerf_launch_count()
+        with torch.no_grad():
+            parts = [(self._fwd_bwd, self._update)] if self._world() == 1 else [(self._fwd_bwd,), (self._update,)]
+            for fns in parts:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    for fn in fns:
+                        self._keep.append(fn())
+                pool = g.pool()
+                self._graphs.append(g)
+        launches_after = dll().nerf_launch_count()
+        torch.cuda.synchronize(self.dev)
+        with torch.no_grad():
+            m.flat_params.copy_(snap[0]); opt._m.copy_(snap[1]); opt._v.copy_(snap[2]); self.state.copy_(snap[3])
+            if r_is_bf16(self.renderer):
+                m.mark_dirty()
+                m.packed_weights()
+        torch.cuda.set_rng_state(rng, self.dev)
+        self._ptrs = self._live_ptrs()
+        self.launches_per_step = int(launches_after - launches0)      # libnerf_b200 kernels in one replay
+
+    # ---- public ----------------------------------------------------------------------------------------
+    def load_batch(self, rays_o, rays_d, target):
+        """Copy one batch into the step's static buffers (device or pinned-host sources, async)."""
+        for dst, src in ((self.rays_o, rays_o), (self.rays_d, rays_d), (self.target, target)):
+            if src is not dst:
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise RuntimeError(f"TrainStep: batch shape {tuple(src.shape)} != captured shape {tuple(dst.shape)}")
+                dst.copy_(src, non_blocking=True)
+
+    def __call__(self, rays_o=None, rays_d=None, target=None):
+        if rays_o is not None:
+            self.load_batch(rays_o, rays_d, target)
+        self._push_state()
+        m = self.model
+        if self.use_graph and self._ptrs != self._live_ptrs():
+            self.recapture()                                      # model moved / buffers re-created since capture
+        if r_is_bf16(self.renderer):
+            m.packed_weights()                                    # host-side check; re-packs only after an external weight load
+        with torch.no_grad():
+            if self.use_graph:
+                self._graphs[0].replay()
+                if len(self._graphs) > 1:
+                    self._allreduce()
+                    self._graphs[1].replay()
+            else:
+                self._keep = self._eager()
+        # host mirrors: FlatAdam's counter, the LR scheduler's "optimizer.step() was called" flag
+        self.opt._step += 1
+        self._step_pushed = self.opt._step
+        self.opt._opt_called = True
+        return self._loss
+
+    @property
+    def loss(self):
+        return self._loss
+
+    @property
+    def metrics(self):
+        """device tensor [loss, psnr, grad_norm] (float64) of the last step; no sync."""
+        return self.state[_ST_LOSS:_ST_GNORM + 1]
+
+    def read_metrics(self):
+        loss, psnr, gnorm = self.metrics.tolist()
+        return {"loss": loss, "psnr": psnr, "grad_norm": gnorm}
+
+
+def r_is_bf16(renderer):
+    return renderer._prec() == _lib.PREC_BF16
+
+
+def psnr_from_mse(mse):
+    """skimage.metrics.peak_signal_noise_ratio(data_range=1.0) given the mse (scripts/train.py:33-37)."""
+    return 10.0 * math.log10(1.0 / mse) if mse > 0 else float("inf")

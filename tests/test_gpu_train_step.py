@@ -1,0 +1,184 @@
+"""TrainStep: the reference's loop body scripts/train.py:374-388 as a fixed
+launch sequence / CUDA graph.  Parity bars:
+
+  * eager TrainStep vs the autograd path (NeRFRenderer._render_rays + loss.backward() + FlatAdam,
+    i.e. the reference's own loop on the drop-in classes): same kernels in the same order, so the
+    loss of step 1 is bit-identical and the gradient of step 1 agrees to 1e-5 relative L2 (the
+    wgrad kernel's fp32 atomics may reorder); losses of 3 steps agree to 2e-4 relative;
+    parameters after 3 steps: >= 85 % within 2e-5 and all within 2.1e-3 (= the bars of
+    test_optimizer_steps_match_reference: Adam's m/sqrt(v) turns a reordered-atomics difference
+    in a near-zero gradient into an O(lr) difference in that weight);
+  * graph replay vs eager TrainStep: same bars, same RNG stream (perturb=1 draws included);
+  * fp32 check mode vs the reference's golden training run (tests/golden/train_r32.npz): the same
+    bars as test_optimizer_steps_match_reference;
+  * metrics: loss == mean((rgb-target)^2), psnr == 10 log10(1/loss) (skimage, data_range 1),
+    grad_norm == sqrt(sum_p |p.grad|^2) (scripts/train.py:60-67) to 1e-6 relative;
+  * the learning-rate schedule (StepLR, scripts/train.py:260) advances on the device state block.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV, torch.float32)
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nerf_mlp_b200
+    return nerf_mlp_b200
+
+
+def make(nb, seed, precision, perturb, lr=5e-4):
+    m = nb.NeRFMLP(precision=precision)
+    p = O.init_params(seed)
+    m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()})
+    m = m.to(DEV)
+    r = nb.NeRFRenderer(m, DEV, perturb=perturb)
+    return m, r, nb.FlatAdam(m, lr=lr)
+
+
+def batch(R, seed):
+    o, d = O.random_rays(R, seed)
+    tgt = np.random.default_rng(seed + 1).uniform(0, 1, (R, 3)).astype(np.float32)
+    return T(o), T(d), T(tgt)
+
+
+def autograd_steps(nb, m, r, opt, o, d, tgt, n, sched=None, grads=None):
+    losses = []
+    for _ in range(n):
+        loss = nb.ops.mse_loss(r._render_rays(o, d)["rgb_map"], tgt)
+        opt.zero_grad()
+        loss.backward()
+        if grads is not None and not grads:
+            grads.append(m.flat_grad.detach().cpu().numpy().copy())
+        opt.step()
+        if sched is not None:
+            sched.step()
+        losses.append(float(loss.detach()))
+    return losses
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("perturb", [0.0, 1.0])
+def test_eager_and_graph_match_autograd_path(nb, precision, perturb):
+    R, n = 200, 3
+    o, d, tgt = batch(R, 7)
+    runs = {}
+    for kind in ("autograd", "eager", "graph"):
+        m, r, opt = make(nb, 11, precision, perturb)
+        g1 = []
+        if kind == "autograd":
+            torch.manual_seed(123)
+            losses = autograd_steps(nb, m, r, opt, o, d, tgt, n, grads=g1)
+        else:
+            step = nb.TrainStep(r, opt, R, graph=(kind == "graph"))
+            torch.manual_seed(123)
+            losses = []
+            for i in range(n):
+                losses.append(float(step(o, d, tgt)))
+                if i == 0:
+                    g1.append(m.flat_grad.detach().cpu().numpy().copy())
+            assert opt._step == n
+        runs[kind] = (losses, m.flat_params.detach().cpu().numpy().copy(), g1[0])
+    ref_l, ref_p, ref_g = runs["autograd"]
+    assert ref_l[-1] < ref_l[0]
+    for kind in ("eager", "graph"):
+        l, p, g = runs[kind]
+        assert l[0] == ref_l[0], (kind, l, ref_l)                    # forward path is deterministic
+        assert np.linalg.norm(g - ref_g) <= 1e-5 * np.linalg.norm(ref_g), kind
+        np.testing.assert_allclose(l, ref_l, rtol=2e-4, err_msg=kind)
+        np.testing.assert_allclose(p, ref_p, atol=2.1e-3, err_msg=kind)
+        assert np.mean(np.abs(p - ref_p) <= 2e-5) > 0.85, kind
+
+
+def test_construction_does_not_train(nb):
+    m, r, opt = make(nb, 3, "bf16", 1.0)
+    before = m.flat_params.clone()
+    torch.manual_seed(5)
+    a = torch.rand(4, device=DEV)
+    torch.manual_seed(5)
+    step = nb.TrainStep(r, opt, 64)
+    b = torch.rand(4, device=DEV)
+    assert torch.equal(before, m.flat_params) and torch.equal(a, b)
+    assert opt._step == 0 and float(step.state[5]) == 0.0
+    assert float(opt._m.abs().max()) == 0.0
+
+
+def test_fp32_step_matches_reference_golden(nb):
+    """Two graph-replayed steps reproduce the reference's own training run (same bars as
+    test_optimizer_steps_match_reference in test_gpu_mlp_render.py)."""
+    g = load_golden("train_r32")
+    m, r, opt = make(nb, int(g["seed"]), "fp32", 0.0)
+    R = g["rays_o"].shape[0]
+    step = nb.TrainStep(r, opt, R)
+    o, d, tgt = T(g["rays_o"]), T(g["rays_d"]), T(g["target"])
+    for i in (1, 2):
+        loss = float(step(o, d, tgt))
+        assert abs(loss - float(g[f"loss_step{i - 1}"])) < 1e-4      # golden steps are 0-based
+        flat = m.flat_params.detach().cpu().numpy()
+        ref = g[f"params_after_step{i}_sub"]
+        np.testing.assert_allclose(flat[::101], ref, atol=2.1e-3)
+        assert np.mean(np.abs(flat[::101] - ref) < 2e-5) > 0.97
+
+
+def test_metrics_and_lr_schedule(nb):
+    R = 128
+    o, d, tgt = batch(R, 21)
+    m, r, opt = make(nb, 11, "bf16", 0.0, lr=1e-3)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.1)
+    step = nb.TrainStep(r, opt, R)
+    m2, r2, opt2 = make(nb, 11, "bf16", 0.0, lr=1e-3)
+    sched2 = torch.optim.lr_scheduler.StepLR(opt2, step_size=2, gamma=0.1)
+    for i in range(5):
+        loss = step(o, d, tgt)
+        sched.step()
+        got = step.read_metrics()
+        rgb = step.outputs["rgb_map"]
+        mse = float(torch.mean((rgb.double() - tgt.double()) ** 2))
+        assert abs(got["loss"] - float(loss)) == 0.0
+        assert abs(got["loss"] - mse) <= 1e-6 * mse
+        assert abs(got["psnr"] - 10.0 * math.log10(1.0 / mse)) < 1e-4
+        gn = math.sqrt(sum(float(p.grad.norm(2)) ** 2 for p in m.parameters()))      # scripts/train.py:60-67
+        assert abs(got["grad_norm"] - gn) <= 1e-5 * gn
+        assert float(step.state[5]) == i + 1
+        autograd_steps(nb, m2, r2, opt2, o, d, tgt, 1, sched2)
+        assert float(step.state[0]) == pytest.approx(1e-3 * 0.1 ** (i // 2), rel=1e-12)   # lr used by step i
+        pa, pb = m.flat_params.cpu().numpy(), m2.flat_params.cpu().numpy()
+        np.testing.assert_allclose(pa, pb, atol=4.2e-3)
+        assert np.mean(np.abs(pa - pb) <= 2e-5) > 0.85
+    assert opt.param_groups[0]["lr"] == pytest.approx(opt2.param_groups[0]["lr"])
+
+
+def test_external_weight_load_is_seen_by_the_graph(nb):
+    R = 64
+    o, d, tgt = batch(R, 31)
+    m, r, opt = make(nb, 11, "bf16", 0.0)
+    step = nb.TrainStep(r, opt, R)
+    l0 = float(step(o, d, tgt))
+    p = O.init_params(12)
+    m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()})
+    m3, r3, opt3 = make(nb, 12, "bf16", 0.0)
+    ref = float(nb.ops.mse_loss(r3._render_rays(o, d)["rgb_map"], tgt))
+    l1 = float(step(o, d, tgt))
+    assert l1 == ref and l1 != l0
+
+
+def test_shape_and_config_errors(nb):
+    m, r, opt = make(nb, 3, "bf16", 1.0)
+    step = nb.TrainStep(r, opt, 32, graph=False)
+    o, d, tgt = batch(16, 1)
+    with pytest.raises(RuntimeError):
+        step(o, d, tgt)
+    r.coarse_grad = True
+    with pytest.raises(NotImplementedError):
+        nb.TrainStep(r, opt, 32)

@@ -45,6 +45,15 @@ def test_argument_checks_do_not_need_a_gpu():
     assert rc != 0 and b"precision" in dll.nerf_last_error()
 
 
+def test_train_step_has_no_cpu_fallback():
+    m = nb.NeRFMLP()
+    r = nb.NeRFRenderer(m, "cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        nb.TrainStep(r, nb.FlatAdam(m), 16)
+    dll = nb._lib.dll()
+    assert dll.nerf_train_prepare(None, None, None, 0, None) != 0 and b"nerf_train_prepare" in dll.nerf_last_error()
+
+
 def test_model_surface_matches_reference():
     torch.manual_seed(0)
     m = nb.NeRFMLP()
