@@ -144,6 +144,27 @@ int nerf_train_prepare(double* state, const float* loss, const float* flat_grads
 int nerf_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                        const double* state, void* stream);
 
+/* ---- the callers either side of the path, on the device ----------
+ * nerf_generate_rays: rays (and optionally target colours) of n flat ray ids
+ *   id = img*H*W + j*W + i  (the row order of NeRFDataset.all_rays_*, nerfmlp/data.py:76-97):
+ *   rays_d = [(i-W/2)/focal, -(j-H/2)/focal, -1] @ pose[:3,:3].T in float64, rounded once to float32
+ *   (data.py:80,86 followed by .float() at :101); rays_o = pose[:3,3] (:87).
+ *   idx != NULL: gather of a training batch (replaces Dataset.__getitem__ data.py:99-104 + DataLoader
+ *   collate, scripts/train.py:219,368-371); idx == NULL: the contiguous ids first..first+n-1, e.g. all
+ *   pixels of one view for rendering (scripts/render_example.py:245-250), or one rank's shard of it.
+ *   Target colour (rgb_out nullable): from rgb_lin[n_poses,H,W,3] (already preprocessed linear RGB) or
+ *   from raw rgba[n_poses,H,W,4] bytes with the reference's preprocessing fused: /255, white-background
+ *   alpha composite in float64 (data.py:47-55), sRGB->linear in float32 (:8-22,62).
+ *   poses: [n_poses,4,4] row-major float32 on the device. */
+int nerf_generate_rays(const float* poses, int n_poses, int H, int W, double focal, const int64_t* idx,
+                       int64_t first, int64_t n, float* rays_o, float* rays_d, const uint8_t* rgba,
+                       const float* rgb_lin, int white_bkgd, float* rgb_out, void* stream);
+
+/* Output post-processing of scripts/render_example.py:256-271 on n floats: * brightness,
+ * optional linear->sRGB (:12-26, float32), clip to [0,1], * 255, truncate to uint8. */
+int nerf_postprocess_rgb8(const float* rgb, int64_t n, float brightness, int to_srgb, uint8_t* out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

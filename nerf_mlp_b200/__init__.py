@@ -9,7 +9,8 @@ from .model import NeRFMLP, PositionalEncoding
 from .renderer import NeRFRenderer
 from .optim import FlatAdam
 from .train import TrainStep
-from . import dist
+from . import checkpoint, data, dist
+from .data import DeviceRayDataset
 
 __version__ = "1.0.0"
-__all__ = ["NeRFMLP", "NeRFRenderer", "PositionalEncoding", "FlatAdam", "TrainStep", "dist"]
+__all__ = ["NeRFMLP", "NeRFRenderer", "PositionalEncoding", "FlatAdam", "TrainStep", "DeviceRayDataset", "checkpoint", "data", "dist"]

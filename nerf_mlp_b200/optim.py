@@ -50,16 +50,55 @@ class FlatAdam(torch.optim.Optimizer):
         model.mark_dirty()
         return loss
 
+    # ---- checkpoint interop: the reference saves torch.optim.Adam's state_dict ------------------
+    # (scripts/train.py:471-475 'optimizer_state_dict') and resumes from it (:303-306).  FlatAdam
+    # writes and reads exactly that format -- per-parameter {'step','exp_avg','exp_avg_sq'} in
+    # state_dict order -- so checkpoints move between the reference and this package both ways.
     def state_dict(self):
         sd = super().state_dict()
-        sd["flat"] = {"step": self._step, "exp_avg": self._m, "exp_avg_sq": self._v}
+        state = {}
+        if self._m is not None and self._step > 0:
+            step = torch.tensor(float(self._step), dtype=torch.float32)
+            for i, (m, v) in enumerate(zip(self.model._views_of(self._m), self.model._views_of(self._v))):
+                state[i] = {"step": step.clone(), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+        sd["state"] = state
         return sd
 
     def load_state_dict(self, sd):
-        flat = sd.get("flat")
-        super().load_state_dict({k: v for k, v in sd.items() if k != "flat"})
+        state = sd.get("state", {})
+        flat = sd.get("flat")                      # layout written by earlier versions of this class
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.model._param_list):
+            raise ValueError("FlatAdam.load_state_dict: expected one param group over the model's 24 tensors")
+        g = groups[0]
+        if g.get("weight_decay", 0) != 0 or g.get("amsgrad", False) or g.get("maximize", False):
+            raise NotImplementedError("FlatAdam implements plain Adam (no weight decay / amsgrad / maximize), "
+                                      "the configuration of scripts/train.py:258")
+        super().load_state_dict({"state": {}, "param_groups": groups})
+        self.model._ensure_flat()
+        dev = self.model.flat_params.device
         if flat is not None:
             self._step = int(flat["step"])
-            dev = self.model.flat_params.device
             self._m = None if flat["exp_avg"] is None else flat["exp_avg"].to(dev).clone()
             self._v = None if flat["exp_avg_sq"] is None else flat["exp_avg_sq"].to(dev).clone()
+            return
+        if not state:
+            self._step, self._m, self._v = 0, None, None
+            return
+        ids = g["params"]
+        if any(i not in state for i in ids):
+            raise ValueError("FlatAdam.load_state_dict: optimizer state is missing parameters")
+        steps = {int(float(state[i]["step"])) for i in ids}
+        if len(steps) != 1:
+            raise ValueError(f"FlatAdam.load_state_dict: parameters disagree on the step count {sorted(steps)}")
+        self._step = steps.pop()
+        if self._m is None or self._m.device != dev:
+            self._m = torch.zeros_like(self.model.flat_params)
+            self._v = torch.zeros_like(self.model.flat_params)
+        with torch.no_grad():
+            for i, m, v, p in zip(ids, self.model._views_of(self._m), self.model._views_of(self._v), self.model._param_list):
+                ea, es = state[i]["exp_avg"], state[i]["exp_avg_sq"]
+                if tuple(ea.shape) != tuple(p.shape):
+                    raise ValueError(f"FlatAdam.load_state_dict: state {i} has shape {tuple(ea.shape)}, parameter {tuple(p.shape)}")
+                m.copy_(ea)
+                v.copy_(es)

@@ -86,6 +86,19 @@ class NeRFRenderer:
         rgb_map = torch.cat(results, 0)
         return rgb_map.view(H, W, 3)
 
+    def render_maps(self, rays_o, rays_d, H, W, focal, chunk=1024 * 16):
+        """`render` that keeps everything `_render_rays` returns (the reference's `render` drops the
+        depth / acc / coarse maps, renderer.py:44): dict of (H, W, 3) / (H, W) tensors, no grad."""
+        parts = []
+        for i in range(0, rays_o.shape[0], chunk):
+            with torch.no_grad():
+                parts.append(self._render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk]))
+        out = {}
+        for k in parts[0]:
+            v = torch.cat([p[k] for p in parts], 0)
+            out[k] = v.view(H, W, 3) if v.dim() == 2 else v.view(H, W)
+        return out
+
     def _render_rays(self, rays_o, rays_d):
         rays_o = _lib.f32c(rays_o)
         rays_d = _lib.f32c(rays_d)

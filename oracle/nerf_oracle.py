@@ -422,3 +422,50 @@ def random_rays(R: int, seed: int = 0):
     d = rng.standard_normal((R, 3)).astype(F32)
     d[:, 2] = -np.abs(d[:, 2]) - 1.0
     return o, d
+
+
+# ----------------------------------------------------------------------------------------------
+# Callers either side of the path
+# ----------------------------------------------------------------------------------------------
+def srgb_to_linear(img):
+    """nerfmlp/data.py:8-22 (float32 where/power)."""
+    img = img.astype(np.float32)
+    return np.where(img <= 0.04045, img / 12.92, np.power((img + 0.055) / 1.055, 2.4))
+
+
+def preprocess_rgba(rgba_u8, white_bkgd=True):
+    """nerfmlp/data.py:46-62 without the file I/O: uint8 RGBA [..., 4] -> float32 linear RGB [..., 3]."""
+    img = np.asarray(rgba_u8) / 255.0                                       # float64, data.py:47
+    rgb, alpha = img[..., :3], img[..., 3:]
+    if white_bkgd:
+        rgb = rgb * alpha + (1 - alpha)                                     # data.py:55
+    return srgb_to_linear(rgb)
+
+
+def dataset_rays(poses, H, W, focal):
+    """nerfmlp/data.py:76-94 followed by __getitem__'s .float() (:99-104): per-image ray tables,
+    image-major.  Returns float32 (rays_o [N*H*W,3], rays_d [N*H*W,3])."""
+    i, j = np.meshgrid(np.arange(W), np.arange(H), indexing='xy')
+    dirs = np.stack([(i - W / 2) / focal, -(j - H / 2) / focal, -np.ones_like(i)], -1)
+    ro, rd = [], []
+    for pose in poses:
+        d = (dirs @ pose[:3, :3].T).reshape(-1, 3)
+        ro.append(np.broadcast_to(pose[:3, 3], d.shape))
+        rd.append(d)
+    return np.concatenate(ro, 0).astype(np.float32), np.concatenate(rd, 0).astype(np.float32)
+
+
+def linear_to_srgb(img):
+    """scripts/render_example.py:12-26 (float32 where/power)."""
+    img = img.astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        return np.where(img <= 0.0031308, img * 12.92, 1.055 * np.power(img, 1 / 2.4) - 0.055)
+
+
+def to_uint8(rgb, brightness=1.0, gamma_correction=False):
+    """scripts/render_example.py:256-271: brightness boost, optional linear->sRGB, clip, 8-bit."""
+    rgb = np.asarray(rgb, np.float32)
+    if brightness != 1.0:
+        rgb = rgb * brightness
+    rgb_final = linear_to_srgb(rgb) if gamma_correction else rgb
+    return (np.clip(rgb_final, 0, 1) * 255).astype(np.uint8)

@@ -241,7 +241,66 @@ def adam_case():
     print("adam ok")
 
 
+def data_case(name="data_3x12x12"):
+    """nerfmlp.NeRFDataset (data.py:24-104) on a tiny synthetic Blender-style scene written to a temp
+    dir, and the output post-processing of scripts/render_example.py (:12-26, :256-271)."""
+    import json
+    import tempfile
+    from PIL import Image
+    from nerfmlp import NeRFDataset
+    sys.path.insert(0, "/root/reference/scripts")
+    import render_example as RE
+    rng = np.random.default_rng(77)
+    N, S = 3, 12
+    angle = 0.6911112070083618
+    rgba = rng.integers(0, 256, (N, S, S, 4), dtype=np.uint8)
+    rgba[0, :2, :, 3] = 255          # some fully opaque / fully transparent pixels, some dark ones (linear branch)
+    rgba[1, :2, :, 3] = 0
+    rgba[2, :3, :, :3] = rng.integers(0, 12, (3, S, 3), dtype=np.uint8)
+    poses = []
+    for _ in range(N):
+        q, _r = np.linalg.qr(rng.standard_normal((3, 3)))
+        m = np.eye(4)
+        m[:3, :3] = q
+        m[:3, 3] = rng.standard_normal(3) * 2.0
+        poses.append(m.astype(np.float32))
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "train"))
+        frames = []
+        for i in range(N):
+            Image.fromarray(rgba[i], "RGBA").save(os.path.join(d, "train", f"r_{i}.png"))
+            frames.append({"file_path": f"./train/r_{i}", "transform_matrix": poses[i].astype(np.float64).tolist()})
+        json.dump({"camera_angle_x": angle, "frames": frames}, open(os.path.join(d, "transforms_train.json"), "w"))
+        ds = NeRFDataset(d, split="train", img_wh=(S, S), white_bkgd=True)
+    idx = rng.permutation(len(ds))[:64]
+    items = [ds[int(i)] for i in idx]
+    g = dict(rgba=rgba, poses=np.stack(poses), camera_angle_x=np.array(angle), focal=np.array(ds.focal, np.float64),
+             all_rays_o=torch.from_numpy(np.ascontiguousarray(ds.all_rays_o)).float().numpy(),
+             all_rays_d=torch.from_numpy(np.ascontiguousarray(ds.all_rays_d)).float().numpy(),
+             all_rgbs=torch.from_numpy(np.ascontiguousarray(ds.all_rgbs)).float().numpy(),
+             idx=idx.astype(np.int64),
+             batch_ray_o=torch.stack([it["ray_o"] for it in items]).numpy(),
+             batch_ray_d=torch.stack([it["ray_d"] for it in items]).numpy(),
+             batch_rgb=torch.stack([it["rgb"] for it in items]).numpy())
+    # post-processing, with the reference's own statements (render_example.py:256-271)
+    lin = rng.uniform(0.0, 1.3, (40, 17, 3)).astype(np.float32)
+    lin[0, :, :] = np.linspace(0, 0.006, 17, dtype=np.float32)[:, None]      # around the 0.0031308 branch point
+    g["pp_in"] = lin
+    for boost in (1.0, 1.5):
+        for gamma in (False, True):
+            rgb = lin.copy()
+            if boost != 1.0:
+                rgb = rgb * boost
+            rgb_final = RE.linear_to_srgb(rgb) if gamma else rgb
+            g[f"pp_out_b{boost}_g{int(gamma)}"] = (np.clip(rgb_final, 0, 1) * 255).astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **g)
+    print(name, len(ds), g["all_rays_d"].dtype, g["all_rgbs"].dtype)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "data":
+        data_case()
+        sys.exit(0)
     stage_case()
     render_case("render_det_r96", 96, 1)                                   # config-1 shape, small R
     render_case("render_pinhole_12x12", 144, 2, pinhole=(12, 12))          # render_example.py rays
@@ -252,3 +311,4 @@ if __name__ == "__main__":
     render_case("render_s128_256_r16", 16, 6, N_samples=128, N_importance=256)   # config-5 style
     grad_case()
     adam_case()
+    data_case()

@@ -186,3 +186,71 @@ def test_multi_rank_host_logic_gloo():
     assert sorted(r[0] for r in res) == [0, 1]
     for r in res:
         assert all(r[1:]), r
+
+
+# ---- checkpoint formats ---------------------------------------------------
+def _adam_steps(opt, model, seed, n):
+    g = torch.Generator().manual_seed(seed)
+    for _ in range(n):
+        for p in model.parameters():
+            p.grad = torch.randn(p.shape, generator=g) * 1e-3
+        opt.step()
+
+
+def test_optimizer_state_interchanges_with_torch_adam(tmp_path):
+    """A checkpoint written by the reference's loop (torch.optim.Adam.state_dict(), scripts/train.py:471-475)
+    resumes in FlatAdam, and FlatAdam's state_dict loads into torch.optim.Adam."""
+    torch.manual_seed(1)
+    m_ref = nb.NeRFMLP()
+    opt_ref = torch.optim.Adam(m_ref.parameters(), lr=5e-4)
+    _adam_steps(opt_ref, m_ref, 3, 2)
+    path = tmp_path / "metrics_latest.pth"
+    torch.save({"model_state_dict": m_ref.state_dict(), "optimizer_state_dict": opt_ref.state_dict(),
+                "metrics": {"step": 2, "best_val_psnr": 12.5}}, path)
+    m = nb.NeRFMLP()
+    opt = nb.FlatAdam(m, lr=1e-3)
+    metrics = nb.checkpoint.load_checkpoint(path, m, opt, map_location="cpu")
+    assert metrics["step"] == 2 and opt._step == 2 and opt.param_groups[0]["lr"] == 5e-4
+    assert torch.equal(m.flat_params, m_ref.flat_params)
+    for i, (mv, vv) in enumerate(zip(m._views_of(opt._m), m._views_of(opt._v))):
+        st = opt_ref.state[opt_ref.param_groups[0]["params"][i]]
+        assert torch.equal(mv, st["exp_avg"]) and torch.equal(vv, st["exp_avg_sq"])
+    # and back: FlatAdam -> file -> torch.optim.Adam continues identically to the uninterrupted run
+    path2 = tmp_path / "from_flat.pth"
+    nb.checkpoint.save_checkpoint(path2, m, opt, {"step": 2})
+    ck = torch.load(path2)
+    assert set(ck) == {"model_state_dict", "optimizer_state_dict", "metrics"}
+    assert list(ck["model_state_dict"]) == list(O.PARAM_NAMES)
+    m2 = nb.NeRFMLP()
+    m2.load_state_dict(ck["model_state_dict"])
+    opt2 = torch.optim.Adam(m2.parameters(), lr=1.0)
+    opt2.load_state_dict(ck["optimizer_state_dict"])
+    _adam_steps(opt_ref, m_ref, 9, 1)
+    _adam_steps(opt2, m2, 9, 1)
+    assert torch.equal(m2.flat_params, m_ref.flat_params)
+    # unsupported Adam variants are refused, not silently ignored
+    bad = opt_ref.state_dict()
+    bad["param_groups"][0]["weight_decay"] = 0.1
+    with pytest.raises(NotImplementedError):
+        opt.load_state_dict(bad)
+
+
+def test_weight_files(tmp_path):
+    """.pth state_dict and the official .npy weight list (render_example.py:166-208, model.py:83-127)."""
+    p = O.init_params(4)
+    m = nb.NeRFMLP()
+    m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()})
+    nb.checkpoint.save_weights(m, tmp_path / "model_best.pth")
+    m2 = nb.checkpoint.load_weights(nb.NeRFMLP(), tmp_path / "model_best.pth", map_location="cpu")
+    assert torch.equal(m2.flat_params, m.flat_params) and m2._dirty
+    # official list order: 8 trunk pairs, bottleneck, view, rgb, sigma; arrays are [in, out]
+    names = [f"pts_linears.{i}" for i in range(8)] + ["bottleneck_linear", "view_linear", "rgb_linear", "sigma_linear"]
+    arrs = []
+    for n in names:
+        arrs += [p[n + ".weight"].T.copy(), p[n + ".bias"].copy()]
+    obj = np.empty(len(arrs), dtype=object)
+    for i, a in enumerate(arrs):
+        obj[i] = a
+    np.save(tmp_path / "model_fine.npy", obj, allow_pickle=True)
+    m3 = nb.checkpoint.load_weights(nb.NeRFMLP(), str(tmp_path / "model_fine.npy"))
+    assert torch.equal(m3.flat_params, m.flat_params)
