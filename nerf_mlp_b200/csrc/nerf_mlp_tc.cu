@@ -302,13 +302,20 @@ __device__ __forceinline__ void fwd_prologue(const TcArgs& a, int64_t row, int m
 }
 
 // ReLU mask of 32 fp32 accumulators, one funnel shift per element: bit j = !sign(r[j]).
+// Four independent 8-bit chains (a single 32-long dependent chain was the top stall of the
+// save-mode epilogue), merged with two byte permutes.
 // (An accumulator that is exactly +0 counts as active; its gradient contribution is multiplied by
 // a zero activation downstream only in the weight gradient, and the event has measure zero.)
 __device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&r)[32]) {
-  uint32_t w = 0;
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
 #pragma unroll
-  for (int j = 31; j >= 0; --j) w = __funnelshift_l(r[j], w, 1);     // w = (w << 1) | (r[j] >> 31)
-  return ~w;
+  for (int j = 7; j >= 0; --j) {                                     // w = (w << 1) | (r[j] >> 31)
+    w0 = __funnelshift_l(r[j], w0, 1);
+    w1 = __funnelshift_l(r[8 + j], w1, 1);
+    w2 = __funnelshift_l(r[16 + j], w2, 1);
+    w3 = __funnelshift_l(r[24 + j], w3, 1);
+  }
+  return ~(__byte_perm(w0, w1, 0x1140) | __byte_perm(w2, w3, 0x4011));   // bytes: w0, w1, w2, w3 (upper bytes of each are 0)
 }
 
 // kBwd = false: forward (kSave: also write the tensors the backward needs); kBwd = true: dgrad chain
@@ -578,11 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), head[c0 + j], sigma);
               }
-              if (kSave) {
-                const uint32_t w = relu_mask32(r);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) if ((c0 >> 5) == i) mkw[i] = w;
-              }
+              if (kSave) mkw[c0 >> 5] = relu_mask32(r);
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 uint4 o;
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             {                                            // two register buffers: the next chunk's tcgen05.ld is in
               uint32_t ra[32], rb[32];                   // flight while the current chunk is converted and stored
               tmem_ld32(taddr, ra);
-#pragma unroll 1
+#pragma unroll                                           // static c0: the mask words stay in registers
               for (int c0 = 0; c0 < 256; c0 += 64) {
                 tmem_ld_wait();
                 tmem_ld32(taddr + c0 + 32, rb);
@@ -744,17 +747,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           tc_fence_after();
           stores_drained();
           tile_writable();
-#pragma unroll 1
-          for (int c0 = 0; c0 < 256; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(taddr + c0, r);
-            tmem_ld_wait();
-            const uint32_t mw = mws[c0 >> 5];
+          // one 32-column chunk: (+ sigma term) -> ReLU mask -> bf16 -> swizzled store
+          auto bchunk = [&](const uint32_t (&r)[32], int c0, uint32_t mw, bool with_sigma) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float x = __uint_as_float(r[j]);
-              if (g == 1) x = fmaf(dr.w, head[c0 + j], x);          // + d_sigma * w_sigma  (model.py:69)
+              if (with_sigma) x = fmaf(dr.w, head[c0 + j], x);      // + d_sigma * w_sigma  (model.py:69)
               v[j] = ((mw >> j) & 1u) ? x : 0.f;
             }
 #pragma unroll
@@ -765,7 +764,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
               const int k = c0 + 8 * c;
               *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
             }
-          }
+          };
+          auto bpass = [&](bool with_sigma) {            // two register buffers, as in the forward epilogue
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
+#pragma unroll
+            for (int c0 = 0; c0 < 256; c0 += 64) {
+              tmem_ld_wait();
+              tmem_ld32(taddr + c0 + 32, rb);
+              bchunk(ra, c0, mws[c0 >> 5], with_sigma);
+              tmem_ld_wait();
+              if (c0 + 64 < 256) tmem_ld32(taddr + c0 + 64, ra);
+              bchunk(rb, c0 + 32, mws[(c0 >> 5) + 1], with_sigma);
+            }
+          };
+          if (g == 1) bpass(true); else bpass(false);
           tc_fence_before();
           fence_proxy_async();
           if (g < kNumGemms - 1) act_arrive();
