@@ -26,6 +26,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 FLOP_PER_ROW_FWD = 1186816          # un-padded MACs x 2
 FLOP_PER_ROW_BWD = 2302208

@@ -50,6 +50,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // Instruction descriptor: bf16 x bf16 -> f32, M=128, both operands MN-major (bits 15 / 16)
 __host__ __device__ constexpr uint32_t make_idesc_mn(int N) {
   return make_idesc_bf16(128, N) | (1u << 15) | (1u << 16);
@@ -164,13 +168,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       for (int h = 0; h < job.mh; ++h) {
         const int mrow = h * 128 + q * 32 + lane;          // output feature
         float* orow = job.out + (int64_t)mrow * job.ld_out;
+        // rows of dW that start 16-byte aligned with a multiple-of-4 width take red.global.add.v4.f32
+        // (a quarter of the L2 reduction operations of the split-K tail)
+        const bool vec = ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) && (job.ncols & 3) == 0;
         for (int c0 = 0; c0 < job.n; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * 256 + c0, r);
           tmem_ld_wait();
+          if (vec) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < job.ncols) atomicAdd(orow + c0 + j, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; j += 4)
+              if (c0 + j < job.ncols)
+                red_add_v4(orow + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                           __uint_as_float(r[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < job.ncols) atomicAdd(orow + c0 + j, __uint_as_float(r[j]));
+          }
         }
       }
       tc_fence_before();
@@ -319,13 +334,30 @@ int mlp_tc_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t 
     nblocks += (int)s;
   }
   jb.n = nj;
+  // The two tiny heads run on CUDA cores and read tensors the tensor-core jobs do not (hv, and h7
+  // a second time); they are forked onto an internal side stream so that they fill the HBM-bound
+  // wgrad kernel's ramp-up / tail instead of adding 40 us after it.  Fork and join are event
+  // dependencies (capturable in a CUDA graph, no host synchronisation); stream and events are
+  // created once per device on the first call.
+  static cudaStream_t side[16] = {};
+  static cudaEvent_t ev_fork[16] = {}, ev_join[16] = {};
+  int dev = 0;
+  NERF_CUDA(cudaGetDevice(&dev));
+  NERF_CHECK_ARG(dev >= 0 && dev < 16, "mlp_tc_wgrad: device ordinal %d out of range", dev);
+  if (side[dev] == nullptr) {
+    NERF_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+    NERF_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+    NERF_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+  }
+  NERF_CUDA(cudaEventRecord(ev_fork[dev], st));
+  NERF_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
   wgrad_tc_kernel<<<nblocks, kWgThreads, kWgSmemBytes, st>>>(jb, L.Mp);
   NERF_LAUNCH_CHECK("wgrad_tc_kernel");
-
-  // ---- CUDA-core piece: the two tiny heads ----
-  heads_wgrad_kernel<<<ceil_div(M, (int64_t)kHeadsWarps * kHeadsRowsPerWarp), 32 * kHeadsWarps, 0, st>>>(
+  heads_wgrad_kernel<<<ceil_div(M, (int64_t)kHeadsWarps * kHeadsRowsPerWarp), 32 * kHeadsWarps, 0, side[dev]>>>(
       d_raw, hv, ACT(7), M, grads);
   NERF_LAUNCH_CHECK("heads_wgrad_kernel");
+  NERF_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
+  NERF_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
   return 0;
 }
 
