@@ -38,15 +38,10 @@
 namespace nerf {
 using namespace ptx;
 
-#ifdef NERF_STORE_WARPS                           // measured: no gain (the copy-out cost is SMEM bandwidth, not issue slots)
-constexpr bool kStoreWarps = true;
-constexpr int kThreads = 416;                     // producer, 2 mma issuers, 2 x 4 compute warps, 2 store warps
-#else
-constexpr bool kStoreWarps = false;
-constexpr int kThreads = 352;                     // producer, 2 mma issuers, 2 x 4 compute warps
-#endif
+// Measured and dropped: dedicated store warps and TMA bulk stores for the tile-image saves (both
+// slower than the per-warp coalesced copies: bulk S2G 0.34 vs 0.31 ms on the 196 608-row save pass).
+constexpr int kThreads = 352;                     // producer, 2 mma issuers, 8 prologue/epilogue warps
 constexpr int kFirstComputeWarp = 3;
-constexpr int kFirstStoreWarp = 11;               // warp 11 -> tile A, warp 12 -> tile B (save modes only)
 constexpr int kNumGemmsFwd = 10, kNumGemmsBwd = 9;
 
 // ---- shared memory map (bytes) ------------------------------------------------------------------
@@ -60,7 +55,7 @@ constexpr int kOnesBytes = 256;
 constexpr int kOffHead = kOffOnes + kOnesBytes;              // w_sigma[256] w_rgb[3][128] b_sigma b_rgb[3]
 constexpr int kHeadFloats = 256 + 384 + 4;
 constexpr int kOffBar = kOffHead + kHeadFloats * 4;
-constexpr int kNumBars = 3 * (2 * kRing) + 5 + (kStoreWarps ? 4 : 0);   // sized for the 2-CTA variant (ring twice as deep)
+constexpr int kNumBars = 3 * (2 * kRing) + 5;      // sized for the 2-CTA variant (ring twice as deep)
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 8;
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
@@ -322,6 +317,7 @@ __device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&r)[32]) {
 template <bool kBwd, bool kSave, int kCtas>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr bool kShared = !kBwd && !kSave;             // all eight compute warps share every epilogue
   constexpr int kRingK = kRing * kCtas;                 // ring slots per CTA (same bytes, half-size slots in pair mode)
   constexpr int kSlotK = kSlotBytes / kCtas;            // bytes of a slot held by one CTA
   const uint32_t rank = (kCtas == 2) ? cluster_ctarank() : 0u;
@@ -339,24 +335,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   auto bar_act = [&](int t) { return bar0 + 8u * (kB0 + t); };             // activations of tile t ready (epilogue -> MMA)
   auto bar_acc = [&](int t) { return bar0 + 8u * (kB0 + 2 + t); };         // accumulator of tile t ready (MMA -> epilogue)
   const uint32_t bar_skew = bar0 + 8u * (kB0 + 4);                         // one-shot: tile A's issuer is kSkew slots in
-  auto bar_wr = [&](int t) { return bar0 + 8u * (kB0 + 5 + t); };          // activation tile t written (epilogue -> store warp)
-  auto bar_cp = [&](int t) { return bar0 + 8u * (kB0 + 7 + t); };          // activation tile t copied out (store warp -> epilogue)
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* head = reinterpret_cast<float*>(smem + kOffHead);
   constexpr int kNumGemms = kBwd ? kNumGemmsBwd : kNumGemmsFwd;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kRingK; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 2); mbar_init(bar_pfull(s), 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), 128 * kCtas); mbar_init(bar_acc(t), 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), (kShared ? 256 : 128) * kCtas); mbar_init(bar_acc(t), 1); }
     mbar_init(bar_skew, 1);
-    if (kStoreWarps) for (int t = 0; t < 2; ++t) { mbar_init(bar_wr(t), 128); mbar_init(bar_cp(t), 1); }
     fence_mbar_init();
   }
   if (warp == 1) {
     if (kCtas == 2) { tmem_alloc2(sbase + kOffTmemPtr, 512); tmem_relinquish2(); }
     else { tmem_alloc(sbase + kOffTmemPtr, 512); tmem_relinquish(); }
   }
-  if (warp >= kFirstComputeWarp && warp < kFirstStoreWarp) {
+  if (warp >= kFirstComputeWarp) {
     const int tid = threadIdx.x - 32 * kFirstComputeWarp;   // 0..255
     // constant A operand of the bias K-step: columns 0,1 = 1, rest 0 (SW32 layout)
     if (tid < 8) {
@@ -466,72 +459,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
         }
       }
     }
-  } else if (warp >= kFirstStoreWarp) {
-    // ================= store warps (save modes): copy finished activation tiles to HBM =================
-    // Takes the 64 KB-per-layer tile-image copies off the epilogue warps: wait until the tile is
-    // written, stream it out (shared and HBM images are byte-identical), tell the epilogue warps
-    // that the tile may be overwritten.
-    if constexpr ((kBwd || kSave) && kStoreWarps) {
-      const int t = warp - kFirstStoreWarp;
-      const uint8_t* src = smem + kOffAct + t * kActBytes + lane * 16;
-      const int64_t ntiles = a.Mp / kTileM;
-      uint32_t ph = 0;
-      for (int unit = unit0; unit < num_units; unit += unit_step) {
-        const int64_t tile = ((int64_t)unit * kCtas + rank) * 2 + t;
-        for (int g = 0; g < 9; ++g) {
-          const int dst_idx = kBwd ? (g == 0 ? 8 : 8 - g) : g;
-          uint8_t* dst = (kBwd ? a.dpre_img : a.act_img) + ((int64_t)dst_idx * ntiles + tile) * 65536 + lane * 16;
-          mbar_wait(bar_wr(t), ph, 1000 + t);
-          ph ^= 1;
-#pragma unroll 1
-          for (int i = 0; i < 128; i += 16) {
-            uint4 v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (i + j) * 512);
-            if (i + 16 == 128) {                           // all reads of the tile are done: release it early
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_cp(t));
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) *reinterpret_cast<uint4*>(dst + (i + j) * 512) = v[j];
-          }
-        }
-      }
-    }
   } else {
     // ================= prologue + epilogue warps =================
-    const int t = (warp - kFirstComputeWarp) >> 2;    // tile A / tile B
+    // Group h (warps 3-6 / 7-10) owns the PROLOGUE of tile h (one row per thread).  Every EPILOGUE is
+    // shared by all eight warps: warp (q, h) drains TMEM lane quadrant q, columns [128h, 128h+128) of
+    // whichever tile's accumulator is ready, so one epilogue takes half as long and the dependent
+    // chain  MMA(l) -> epilogue(l) -> MMA(l+1)  of a tile -- which was measured to pace the kernel,
+    // above all in the save modes -- shortens accordingly; the two warps of a scheduler partition
+    // now overlap each other's TMEM-load / shared-store latencies.
+    const int h = (warp - kFirstComputeWarp) >> 2;    // prologue: own tile; shared epilogues: column half
+    // Epilogue ownership (kShared is a kernel-level constant, see bar_act's arrival count):
+    //   shared   (inference forward)  : every warp works on BOTH tiles, column half h
+    //   separate (save forward, dgrad): warp group h works on tile h only, both column halves in turn.
+    //     Those kernels are bound by the SM's shared-memory / L1 data path (operand reads + tile
+    //     writes + the tile-image copy-out), not by the epilogue latency; sharing measured 7 % slower.
+    const int t_lo = kShared ? 0 : h, t_hi = kShared ? 2 : h + 1;
+    const int ch_lo = kShared ? h : 0, ch_hi = kShared ? h + 1 : 2;
     const int q = warp & 3;                           // TMEM lane quadrant this warp may access
-    const int m = q * 32 + lane;                      // row within the tile
-    uint8_t* xt = smem + kOffX + t * kXBytes;
-    uint8_t* at = smem + kOffAct + t * kActBytes;
-    const uint32_t at_s = sbase + kOffAct + t * kActBytes, xt_s = sbase + kOffX + t * kXBytes;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256;
+    const int m = q * 32 + lane;                      // row within a tile
     constexpr bool kStores = kBwd || kSave;           // does this kernel write tile images to HBM?
-    // Tile-image saves: after the group's 128 threads have written (and proxy-fenced) a tile in
-    // shared memory, thread 0 of the group issues ONE bulk store; before anybody overwrites that
-    // region again, thread 0 waits for the store to have read it and the group re-synchronises.
-    // Per-warp granularity: this warp's 32 rows are one contiguous 4 KB block per 64-feature block,
-    // in shared memory and in the HBM tile image alike.
-    auto stores_drained = [&]() {
-#ifdef NERF_SAVE_BULK
-      if (kStores) {
-        if (lane == 0) bulk_wait_read();
-        __syncwarp();
-      }
-#endif
-    };
-    auto store_tile = [&](uint8_t* dst, uint32_t src, uint32_t bytes) {
+    // Tile-image saves: this warp's 32 rows of one 64-feature block are ONE contiguous 4 KB block, in
+    // shared memory and in the HBM tile image alike, and are written by this warp only -> a
+    // coalesced per-warp copy with warp-level synchronisation.
+    // (Ownership rule: a warp only ever copies out blocks it wrote itself, and the next writer of
+    // those bytes is the same warp, or a warp that has since passed a barrier this warp reached
+    // after the copy.)
+    auto store_blocks = [&](uint8_t* dst, int dst_fb0, const uint8_t* src, int src_fb0, int nfb) {
       __syncwarp();
-      const int nfb = (int)(bytes >> 14);
-#ifdef NERF_SAVE_BULK
-      if (lane == 0) {
-        for (int fb = 0; fb < nfb; ++fb) bulk_s2g(dst + fb * 16384 + q * 4096, src + fb * 16384 + q * 4096, 4096);
-        bulk_commit();
-      }
-#else
-      const uint8_t* sp = smem + (src - sbase) + q * 4096 + lane * 16;
-      uint8_t* dp = dst + q * 4096 + lane * 16;
+      const uint8_t* sp = src + src_fb0 * 16384 + q * 4096 + lane * 16;
+      uint8_t* dp = dst + dst_fb0 * 16384 + q * 4096 + lane * 16;
       for (int fb = 0; fb < nfb; ++fb) {
         uint4 v[8];
 #pragma unroll
@@ -539,178 +495,195 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(dp + fb * 16384 + i * 512) = v[i];
       }
-      __syncwarp();     // lanes read each other's rows: nobody may overwrite the tile before all are done
-#endif
+      __syncwarp();     // lanes read each other's rows: nobody may overwrite them before all are done
     };
-    uint32_t acc_ph = 0, cp_ph = 0;
-    bool store_pending = false;                       // an activation-tile copy by the store warp may be in flight
-    auto tile_writable = [&]() {                      // call before overwriting the activation tile
-      if (kStores && kStoreWarps && store_pending) { mbar_wait(bar_cp(t), cp_ph, 1100 + t); cp_ph ^= 1; store_pending = false; }
+    auto act_arrive = [&](int t) {   // "activations of tile t ready": local, or (peer CTA of a pair) remote at the leader
+      if (kCtas == 2 && rank != 0) mbar_arrive_cluster(mapa(bar_act(t), 0)); else mbar_arrive(bar_act(t));
     };
-    auto tile_written = [&](uint8_t* dst) {           // writers are proxy-fenced; copy the tile image out
-      if (kStores) {
-        if (kStoreWarps) { mbar_arrive(bar_wr(t)); store_pending = true; }
-        else store_tile(dst, at_s, 65536);
-      }
-    };
-    // "activations of tile t ready": local arrive, or (peer CTA of a pair) remote arrive at the leader
-    const uint32_t act_remote = (kCtas == 2 && rank != 0) ? mapa(bar_act(t), 0) : 0u;
-    auto act_arrive = [&]() {
-      if (kCtas == 2 && rank != 0) mbar_arrive_cluster(act_remote); else mbar_arrive(bar_act(t));
-    };
+    uint32_t acc_ph = 0u;                             // bit t = phase of bar_acc(t)
+    const int64_t ntiles = a.Mp / kTileM;
+    // cross-warp scratch for the head partial sums (forward, last layer): the 4 KB of tile A's x-tile
+    // that hold rows 32q..32q+31 -- no MMA reads them after layer 5, warp (q,1) writes, warp (q,0)
+    // reads and is also the next to overwrite them (its prologue rows)
+    float4* xchg = reinterpret_cast<float4*>(smem + kOffX + q * 4096);
     for (int unit = unit0; unit < num_units; unit += unit_step) {
-      const int64_t tile = ((int64_t)unit * kCtas + rank) * 2 + t;
-      const int64_t row = tile * kTileM + m;
-      const bool valid = row < a.M;
-      const int64_t ntiles = a.Mp / kTileM;
+      const int64_t tile0 = ((int64_t)unit * kCtas + rank) * 2;
       if constexpr (!kBwd) {
         // ------------------------------ forward ------------------------------
-        stores_drained();
-        fwd_prologue(a, row, m, xt);
-        fence_proxy_async();
-        act_arrive();
-        if (kSave) store_tile(a.xenc_img + tile * 16384, xt_s, 16384);
-        float sigma = head[640];
+        {                                                  // prologue of the own tile
+          const int64_t row = (tile0 + h) * kTileM + m;
+          uint8_t* xt = smem + kOffX + h * kXBytes;
+          if (kShared) act_arrive(1 - h);                  // nothing to write for the other tile
+          fwd_prologue(a, row, m, xt);
+          fence_proxy_async();
+          act_arrive(h);
+          if (kSave) store_blocks(a.xenc_img + (tile0 + h) * 16384, 0, xt, 0, 1);
+        }
+        float sigma0 = 0.f, sigma1 = 0.f;                  // partial sigma head of (tile A / B, own column half)
         for (int g = 0; g < kNumGemms; ++g) {
-          mbar_wait(bar_acc(t), acc_ph, 400 + t);
-          acc_ph ^= 1;
-          tc_fence_after();
-          stores_drained();
-          tile_writable();
-          if (g < 9) {
-            uint32_t mkw[8];
-            // one 32-column chunk: sigma head, ReLU mask, convert, swizzled store
-            auto chunk = [&](const uint32_t (&r)[32], int c0) {
-              if (g == 7) {                              // sigma head from fp32 post-ReLU activations (model.py:69)
+#pragma unroll 1
+          for (int t = t_lo; t < t_hi; ++t) {
+            float sigma = t ? sigma1 : sigma0;
+            const int64_t tile = tile0 + t;
+            const int64_t row = tile * kTileM + m;
+            const bool valid = row < a.M;
+            uint8_t* at = smem + kOffAct + t * kActBytes;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256;
+            mbar_wait(bar_acc(t), (acc_ph >> t) & 1u, 400 + t);
+            acc_ph ^= 1u << t;
+            tc_fence_after();
+            if (g < 9) {
+#pragma unroll 1
+             for (int ch = ch_lo; ch < ch_hi; ++ch) {
+              uint32_t mkw[4];
+              // one 32-column chunk: sigma head, ReLU mask, convert, swizzled store
+              auto chunk = [&](const uint32_t (&r)[32], int c0, int mi) {
+                if (g == 7) {                              // sigma head from fp32 post-ReLU activations (model.py:69)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), head[c0 + j], sigma);
-              }
-              if (kSave) mkw[c0 >> 5] = relu_mask32(r);
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint4 o;
-                if (g != 8) {                            // ReLU on every trunk layer (model.py:65); bottleneck has none (:70)
-                  o.x = pack_bf16x2_relu(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
-                  o.y = pack_bf16x2_relu(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
-                  o.z = pack_bf16x2_relu(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
-                  o.w = pack_bf16x2_relu(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
-                } else {
-                  o.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
-                  o.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
-                  o.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
-                  o.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+                  for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), head[c0 + j], sigma);
                 }
-                const int k = c0 + 8 * c;
-                *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
-              }
-            };
-#ifdef NERF_EPI_SINGLE
-#pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
-              uint32_t r[32];
-              tmem_ld32(taddr + c0, r);
-              tmem_ld_wait();
-              chunk(r, c0);
-            }
-#else
-            {                                            // two register buffers: the next chunk's tcgen05.ld is in
-              uint32_t ra[32], rb[32];                   // flight while the current chunk is converted and stored
-              tmem_ld32(taddr, ra);
-#pragma unroll                                           // static c0: the mask words stay in registers
-              for (int c0 = 0; c0 < 256; c0 += 64) {
-                tmem_ld_wait();
-                tmem_ld32(taddr + c0 + 32, rb);
-                chunk(ra, c0);
-                tmem_ld_wait();
-                if (c0 + 64 < 256) tmem_ld32(taddr + c0 + 64, ra);
-                chunk(rb, c0 + 32);
-              }
-            }
-#endif
-            tc_fence_before();
-            fence_proxy_async();
-            act_arrive();
-            if (kSave) {                                   // off the critical path: the MMAs are already released
-              tile_written(a.act_img + ((int64_t)g * ntiles + tile) * 65536);
-              if (g < 8 && valid) {
-                uint4* mp = reinterpret_cast<uint4*>(a.mask + ((int64_t)g * a.M + row) * 8);
-                mp[0] = make_uint4(mkw[0], mkw[1], mkw[2], mkw[3]);
-                mp[1] = make_uint4(mkw[4], mkw[5], mkw[6], mkw[7]);
-              }
-            }
-          } else {
-            // view layer epilogue: + view bias, ReLU (model.py:73-74), rgb head (:75), output [rgb, sigma] (:77)
-            const int64_t vrow = (valid ? row : (a.M - 1)) / a.vb_div;
-            const float4* vb4 = reinterpret_cast<const float4*>(a.vb + vrow * 128);
-            uint32_t hmw[4];
-            float o0 = head[641], o1 = head[642], o2 = head[643];
-#pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-              uint32_t r[32];
-              tmem_ld32(taddr + c0, r);
-              tmem_ld_wait();
-              float h[32];
-              uint32_t mw = 0;
+                if (kSave) mkw[mi] = relu_mask32(r);
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 b = __ldg(vb4 + (c0 >> 2) + j4);
-                h[4 * j4 + 0] = fmaxf(__uint_as_float(r[4 * j4 + 0]) + b.x, 0.f);
-                h[4 * j4 + 1] = fmaxf(__uint_as_float(r[4 * j4 + 1]) + b.y, 0.f);
-                h[4 * j4 + 2] = fmaxf(__uint_as_float(r[4 * j4 + 2]) + b.z, 0.f);
-                h[4 * j4 + 3] = fmaxf(__uint_as_float(r[4 * j4 + 3]) + b.w, 0.f);
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                o0 = fmaf(h[j], head[256 + c0 + j], o0);
-                o1 = fmaf(h[j], head[384 + c0 + j], o1);
-                o2 = fmaf(h[j], head[512 + c0 + j], o2);
-                if (kSave) mw |= (h[j] > 0.f) ? (1u << j) : 0u;
-              }
-              if (kSave) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) if ((c0 >> 5) == i) hmw[i] = mw;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {             // stage in the (now free) activation tile, feature blocks 0-1
+                for (int c = 0; c < 4; ++c) {
                   uint4 o;
-                  o.x = pack_bf16x2(h[8 * c + 0], h[8 * c + 1]);
-                  o.y = pack_bf16x2(h[8 * c + 2], h[8 * c + 3]);
-                  o.z = pack_bf16x2(h[8 * c + 4], h[8 * c + 5]);
-                  o.w = pack_bf16x2(h[8 * c + 6], h[8 * c + 7]);
+                  if (g != 8) {                            // ReLU on every trunk layer (model.py:65); bottleneck has none (:70)
+                    o.x = pack_bf16x2_relu(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
+                    o.y = pack_bf16x2_relu(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                    o.z = pack_bf16x2_relu(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+                    o.w = pack_bf16x2_relu(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+                  } else {
+                    o.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
+                    o.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                    o.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+                    o.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+                  }
                   const int k = c0 + 8 * c;
                   *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
                 }
-              }
-            }
-            if (valid) *reinterpret_cast<float4*>(a.out + row * 4) = make_float4(o0, o1, o2, sigma);
-            tc_fence_before();
-            if (kSave) {
-              // encoded view direction of this sample as bf16 (operand of view_linear's direction columns), block 2
-              const float* dep = a.de + vrow * 32;
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                if (c < 4 && valid) {
-                  const float4 u0 = __ldg(reinterpret_cast<const float4*>(dep) + 2 * c);
-                  const float4 u1 = __ldg(reinterpret_cast<const float4*>(dep) + 2 * c + 1);
-                  o.x = pack_bf16x2(u0.x, u0.y); o.y = pack_bf16x2(u0.z, u0.w);
-                  o.z = pack_bf16x2(u1.x, u1.y); o.w = pack_bf16x2(u1.z, u1.w);
+              };
+              {                                            // two register buffers: the next chunk's tcgen05.ld is in
+                uint32_t ra[32], rb[32];                   // flight while the current chunk is converted and stored
+                const int cb = 128 * ch;
+                tmem_ld32(taddr + cb, ra);
+#pragma unroll                                             // static offsets: the mask words stay in registers
+                for (int c0 = 0; c0 < 128; c0 += 64) {
+                  tmem_ld_wait();
+                  tmem_ld32(taddr + cb + c0 + 32, rb);
+                  chunk(ra, cb + c0, c0 >> 5);
+                  tmem_ld_wait();
+                  if (c0 + 64 < 128) tmem_ld32(taddr + cb + c0 + 64, ra);
+                  chunk(rb, cb + c0 + 32, (c0 >> 5) + 1);
                 }
-                *reinterpret_cast<uint4*>(at + 2 * 16384 + sw128_off(m, 8 * c)) = o;
               }
-              if (valid) *reinterpret_cast<uint4*>(a.hvmask + row * 4) = make_uint4(hmw[0], hmw[1], hmw[2], hmw[3]);
+              if (kSave && g < 8 && valid)
+                *reinterpret_cast<uint4*>(a.mask + ((int64_t)g * a.M + row) * 8 + 4 * ch) =
+                    make_uint4(mkw[0], mkw[1], mkw[2], mkw[3]);
+             }
+              tc_fence_before();
               fence_proxy_async();
-              store_tile(a.hv_img + tile * 32768, at_s, 32768);
-              store_tile(a.de16_img + tile * 16384, at_s + 2 * 16384, 16384);
+              act_arrive(t);
+              if (g == 7) { if (t) sigma1 = sigma; else sigma0 = sigma; }
+              if (kSave) {                                 // off the critical path: the MMAs are already released
+#pragma unroll 1
+                for (int ch = ch_lo; ch < ch_hi; ++ch)
+                  store_blocks(a.act_img + ((int64_t)g * ntiles + tile) * 65536, 2 * ch, at, 2 * ch, 2);
+              }
+            } else {
+              // view layer epilogue: + view bias, ReLU (model.py:73-74), rgb head (:75), output [rgb, sigma] (:77)
+              // this thread: 64 of the 128 columns
+              const int64_t vrow = (valid ? row : (a.M - 1)) / a.vb_div;
+              const float4* vb4 = reinterpret_cast<const float4*>(a.vb + vrow * 128);
+              float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll 1
+             for (int ch = ch_lo; ch < ch_hi; ++ch) {
+              uint32_t hmw[2];
+#pragma unroll 1
+              for (int ci = 0; ci < 2; ++ci) {
+                const int c0 = 64 * ch + 32 * ci;
+                uint32_t r[32];
+                tmem_ld32(taddr + c0, r);
+                tmem_ld_wait();
+                float hh[32];
+                uint32_t mw = 0;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 b = __ldg(vb4 + (c0 >> 2) + j4);
+                  hh[4 * j4 + 0] = fmaxf(__uint_as_float(r[4 * j4 + 0]) + b.x, 0.f);
+                  hh[4 * j4 + 1] = fmaxf(__uint_as_float(r[4 * j4 + 1]) + b.y, 0.f);
+                  hh[4 * j4 + 2] = fmaxf(__uint_as_float(r[4 * j4 + 2]) + b.z, 0.f);
+                  hh[4 * j4 + 3] = fmaxf(__uint_as_float(r[4 * j4 + 3]) + b.w, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  o0 = fmaf(hh[j], head[256 + c0 + j], o0);
+                  o1 = fmaf(hh[j], head[384 + c0 + j], o1);
+                  o2 = fmaf(hh[j], head[512 + c0 + j], o2);
+                  if (kSave) mw |= (hh[j] > 0.f) ? (1u << j) : 0u;
+                }
+                if (kSave) {
+                  if (ci) hmw[1] = mw; else hmw[0] = mw;
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {           // stage in this warp's own block 2h of the (now free) activation tile
+                    uint4 o;
+                    o.x = pack_bf16x2(hh[8 * c + 0], hh[8 * c + 1]);
+                    o.y = pack_bf16x2(hh[8 * c + 2], hh[8 * c + 3]);
+                    o.z = pack_bf16x2(hh[8 * c + 4], hh[8 * c + 5]);
+                    o.w = pack_bf16x2(hh[8 * c + 6], hh[8 * c + 7]);
+                    *reinterpret_cast<uint4*>(at + 2 * ch * 16384 + sw128_off(m, 32 * ci + 8 * c)) = o;
+                  }
+                }
+              }
+              if (kSave && valid) *reinterpret_cast<uint2*>(a.hvmask + row * 4 + 2 * ch) = make_uint2(hmw[0], hmw[1]);
+             }
+              tc_fence_before();
+              // shared mode: combine the two column halves of the heads: half 1 hands its partial sums to half 0
+              if (kShared) {
+                if (h == 1) xchg[t * 32 + lane] = make_float4(o0, o1, o2, sigma);
+                named_bar_sync(1, 256);
+              }
+              if (!kShared || h == 0) {
+                const float4 p = kShared ? xchg[t * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid)
+                  *reinterpret_cast<float4*>(a.out + row * 4) =
+                      make_float4(o0 + p.x + head[641], o1 + p.y + head[642], o2 + p.z + head[643], sigma + p.w + head[640]);
+              }
+              if (kSave) {
+#pragma unroll 1
+                for (int ch = ch_lo; ch < ch_hi; ++ch) store_blocks(a.hv_img + tile * 32768, ch, at, 2 * ch, 1);
+                if (!kShared || h == 0) {
+                  // encoded view direction of this sample as bf16 (operand of view_linear's direction columns), own block 1
+                  const float* dep = a.de + vrow * 32;
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (c < 4 && valid) {
+                      const float4 u0 = __ldg(reinterpret_cast<const float4*>(dep) + 2 * c);
+                      const float4 u1 = __ldg(reinterpret_cast<const float4*>(dep) + 2 * c + 1);
+                      o.x = pack_bf16x2(u0.x, u0.y); o.y = pack_bf16x2(u0.z, u0.w);
+                      o.z = pack_bf16x2(u1.x, u1.y); o.w = pack_bf16x2(u1.z, u1.w);
+                    }
+                    *reinterpret_cast<uint4*>(at + 1 * 16384 + sw128_off(m, 8 * c)) = o;
+                  }
+                  store_blocks(a.de16_img + tile * 16384, 0, at, 1, 1);
+                }
+              }
             }
           }
         }
       } else {
         // ------------------------------ dgrad chain ------------------------------
-        // prologue: d_hv_pre = (d_rgb . W_rgb) * [hv > 0]  (reference autograd of model.py:73-75)
-        const float4 dr = valid ? __ldg(reinterpret_cast<const float4*>(a.d_raw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
-        stores_drained();
-        tile_writable();
+        float dsig0, dsig1;                                // d_sigma of this thread's row in tile A / tile B
         {
+          // prologue (own tile): d_hv_pre = (d_rgb . W_rgb) * [hv > 0]  (reference autograd of model.py:73-75)
+          const int64_t row = (tile0 + h) * kTileM + m;
+          const bool valid = row < a.M;
+          uint8_t* at = smem + kOffAct + h * kActBytes;
+          const float4 dr = valid ? __ldg(reinterpret_cast<const float4*>(a.d_raw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kShared) {
+            act_arrive(1 - h);
+            // blocks 0-1 of tile 1 were copied out by the group-0 warps in the previous unit's last epilogue
+            named_bar_sync(1, 256);
+          }
           uint4 mw = valid ? __ldg(reinterpret_cast<const uint4*>(a.hvmask) + row) : make_uint4(0u, 0u, 0u, 0u);
           const uint32_t mws[4] = {mw.x, mw.y, mw.z, mw.w};
 #pragma unroll
@@ -719,8 +692,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int n = 8 * c + j;
-              const float g = fmaf(dr.x, head[256 + n], fmaf(dr.y, head[384 + n], dr.z * head[512 + n]));
-              v[j] = ((mws[n >> 5] >> (n & 31)) & 1u) ? g : 0.f;
+              const float gg = fmaf(dr.x, head[256 + n], fmaf(dr.y, head[384 + n], dr.z * head[512 + n]));
+              v[j] = ((mws[n >> 5] >> (n & 31)) & 1u) ? gg : 0.f;
             }
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
@@ -728,67 +701,87 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             const int k = 8 * c;
             *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
           }
+          fence_proxy_async();
+          // copy d_hv out BEFORE releasing the MMAs: in the first epilogue warp (q,0) overwrites blocks 0-1 of
+          // both tiles, and for tile 1 that is not the warp that copies here
+          if (kShared) store_blocks(a.dhv_img + (tile0 + h) * 32768, 0, at, 0, 2);
+          act_arrive(h);
+          if (!kShared) store_blocks(a.dhv_img + (tile0 + h) * 32768, 0, at, 0, 2);
         }
-        fence_proxy_async();
-        act_arrive();
-        store_tile(a.dhv_img + tile * 32768, at_s, 32768);
+        {
+          const int64_t r0 = tile0 * kTileM + m, r1 = r0 + kTileM;
+          dsig0 = r0 < a.M ? __ldg(a.d_raw + r0 * 4 + 3) : 0.f;
+          dsig1 = r1 < a.M ? __ldg(a.d_raw + r1 * 4 + 3) : 0.f;
+        }
         for (int g = 0; g < kNumGemms; ++g) {
           // g = 0: d_bott (no mask) | g = 1: d_h7 (+ sigma term, mask 7) | g >= 2: d_pre_{8-g} (mask 8-g)
           const int ml = 8 - g;                                    // mask layer (g >= 1)
-          uint4 m0 = make_uint4(~0u, ~0u, ~0u, ~0u), m1 = m0;
-          if (g >= 1) {                                            // prefetch the ReLU mask before the accumulator wait
-            const uint4* mp = reinterpret_cast<const uint4*>(a.mask + ((int64_t)ml * a.M + (valid ? row : 0)) * 8);
-            m0 = __ldg(mp); m1 = __ldg(mp + 1);
-          }
-          const uint32_t mws[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
           const int dst = (g == 0) ? 8 : ml;                        // dpre slot: 8 = d_bott, else layer index
-          mbar_wait(bar_acc(t), acc_ph, 400 + t);
-          acc_ph ^= 1;
-          tc_fence_after();
-          stores_drained();
-          tile_writable();
-          // one 32-column chunk: (+ sigma term) -> ReLU mask -> bf16 -> swizzled store
-          auto bchunk = [&](const uint32_t (&r)[32], int c0, uint32_t mw, bool with_sigma) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(r[j]);
-              if (with_sigma) x = fmaf(dr.w, head[c0 + j], x);      // + d_sigma * w_sigma  (model.py:69)
-              v[j] = ((mw >> j) & 1u) ? x : 0.f;
+#pragma unroll 1
+          for (int t = t_lo; t < t_hi; ++t) {
+            const float dsig = t ? dsig1 : dsig0;
+            const int64_t tile = tile0 + t;
+            const int64_t row = tile * kTileM + m;
+            const bool valid = row < a.M;
+            uint8_t* at = smem + kOffAct + t * kActBytes;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256;
+            uint4 m0 = make_uint4(~0u, ~0u, ~0u, ~0u), m1 = m0;       // masks of the column halves this thread handles
+            if (g >= 1) {                                          // prefetched before the accumulator wait
+              const uint4* mp = reinterpret_cast<const uint4*>(a.mask + ((int64_t)ml * a.M + (valid ? row : 0)) * 8);
+              m0 = __ldg(mp + ch_lo);
+              if (!kShared) m1 = __ldg(mp + 1);
             }
+            mbar_wait(bar_acc(t), (acc_ph >> t) & 1u, 400 + t);
+            acc_ph ^= 1u << t;
+            tc_fence_after();
+            // one 32-column chunk: (+ sigma term) -> ReLU mask -> bf16 -> swizzled store
+            auto bchunk = [&](const uint32_t (&r)[32], int c0, uint32_t mw, bool with_sigma) {
+              float v[32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]); o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
-              o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
-              const int k = c0 + 8 * c;
-              *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
-            }
-          };
-          auto bpass = [&](bool with_sigma) {            // two register buffers, as in the forward epilogue
-            uint32_t ra[32], rb[32];
-            tmem_ld32(taddr, ra);
+              for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(r[j]);
+                if (with_sigma) x = fmaf(dsig, head[c0 + j], x);   // + d_sigma * w_sigma  (model.py:69)
+                v[j] = ((mw >> j) & 1u) ? x : 0.f;
+              }
 #pragma unroll
-            for (int c0 = 0; c0 < 256; c0 += 64) {
-              tmem_ld_wait();
-              tmem_ld32(taddr + c0 + 32, rb);
-              bchunk(ra, c0, mws[c0 >> 5], with_sigma);
-              tmem_ld_wait();
-              if (c0 + 64 < 256) tmem_ld32(taddr + c0 + 64, ra);
-              bchunk(rb, c0 + 32, mws[(c0 >> 5) + 1], with_sigma);
+              for (int c = 0; c < 4; ++c) {
+                uint4 o;
+                o.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]); o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+                o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+                const int k = c0 + 8 * c;
+                *reinterpret_cast<uint4*>(at + (k >> 6) * 16384 + sw128_off(m, k & 63)) = o;
+              }
+            };
+            auto bpass = [&](bool with_sigma, int ch, const uint4& mq) {   // two register buffers, as in the forward epilogue
+              const uint32_t mws[4] = {mq.x, mq.y, mq.z, mq.w};
+              uint32_t ra[32], rb[32];
+              const int cb = 128 * ch;
+              tmem_ld32(taddr + cb, ra);
+#pragma unroll
+              for (int c0 = 0; c0 < 128; c0 += 64) {
+                tmem_ld_wait();
+                tmem_ld32(taddr + cb + c0 + 32, rb);
+                bchunk(ra, cb + c0, mws[c0 >> 5], with_sigma);
+                tmem_ld_wait();
+                if (c0 + 64 < 128) tmem_ld32(taddr + cb + c0 + 64, ra);
+                bchunk(rb, cb + c0 + 32, mws[(c0 >> 5) + 1], with_sigma);
+              }
+            };
+#pragma unroll 1
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
+              const uint4 mq = (ch == ch_lo) ? m0 : m1;
+              if (g == 1) bpass(true, ch, mq); else bpass(false, ch, mq);
             }
-          };
-          if (g == 1) bpass(true); else bpass(false);
-          tc_fence_before();
-          fence_proxy_async();
-          if (g < kNumGemms - 1) act_arrive();
-          tile_written(a.dpre_img + ((int64_t)dst * ntiles + tile) * 65536);
+            tc_fence_before();
+            fence_proxy_async();
+            if (g < kNumGemms - 1) act_arrive(t);
+#pragma unroll 1
+            for (int ch = ch_lo; ch < ch_hi; ++ch)
+              store_blocks(a.dpre_img + ((int64_t)dst * ntiles + tile) * 65536, 2 * ch, at, 2 * ch, 2);
+          }
         }
       }
     }
-#ifdef NERF_SAVE_BULK
-    if (kStores && lane == 0) bulk_wait_all();            // every store has landed before the CTA exits
-#endif
   }
   __syncthreads();
   if (kCtas == 2) cluster_sync();                     // the peer may still be signalling this CTA's barriers
