@@ -31,6 +31,13 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 FLOP_PER_ROW_FWD = 1186816          # un-padded MACs x 2
 FLOP_PER_ROW_BWD = 2302208
+# wgrad: every distinct bf16 operand once per sample row: dY = d(pre-act) of 8 trunk
+# layers + d_bottleneck (9 x 512 B) + d_hv (256 B); X = h0..h7 + bottleneck (9 x 512 B) + x_enc (128 B) + dir_enc (128 B)
+WGRAD_ALG_BYTES_PER_ROW = 9 * 512 + 256 + 9 * 512 + 128 + 128
+# measured DRAM traffic (ncu dram__bytes_read.sum + dram__bytes_write.sum), see profiles/
+NCU_BYTES_PER_ROW_FWD_SAVE = 5164.0      # 1.0153 GB on the 196 608-row save-mode launch
+NCU_BYTES_PER_ROW_WGRAD = 10548.0        # 2.0740 GB on the same rows
+NCU_BYTES_FWD_INFER_3145728 = 26.03e6    # whole 3 145 728-row inference launch
 N_SAMPLES, N_IMPORTANCE = 64, 128
 
 
@@ -353,7 +360,11 @@ def main():
         td.all_reduce(e2e_s, op=td.ReduceOp.MAX)
     e2e_val = units_per_step * K / float(e2e_s)
 
-    # --- roofline of the dominant kernel: fused MLP forward (largest launch = fine pass) --------------
+    # --- roofline -----------------------------------------------------------------------------------
+    # render: the dominant kernel is the fused MLP forward (tensor-bound).  train: the largest launch
+    # of the step is the weight-gradient kernel, which -- like the save-mode forward and the dgrad
+    # kernel around it -- is bound by HBM bytes; its roofline is `roofline`, and
+    # the tensor-core view of the fused forward (north_star's "% of bf16 peak") is `roofline_tensor`.
     pk = peaks()
     if stage_acc is not None:
         rows_max = rays * (N_SAMPLES + N_IMPORTANCE)
@@ -365,27 +376,34 @@ def main():
         avg_ms = sum(ms for _, ms in fine) / len(fine)
         mlp_ms_per_step = sum(a.elapsed_time(b) for _, a, b in mlp_events) / K
     achieved = rows_max * FLOP_PER_ROW_FWD / (avg_ms * 1e-3) / 1e12
-    roofline = {"kernel": "mlp_fwd_tc_kernel (fused PE + 8x256 MLP + heads), fine pass" if args.precision == "bf16" else "fp32 check-mode SGEMM chain",
-                "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + ", burst bf16 matmul",
-                "frac_of_sustained": (achieved / pk["bf16_tflops_sustained"]) if pk.get("bf16_tflops_sustained") else None,
-                "rows_per_launch": rows_max, "flop_per_row": FLOP_PER_ROW_FWD, "avg_launch_ms": avg_ms,
-                "mlp_fwd_share_of_step": mlp_ms_per_step / (sum(ms_steps) / K)}
-    # DRAM traffic of that launch from the committed ncu --set full captures (profiles/r01_*_ncu_summary.csv):
-    # inference launch of 3 145 728 rows: 22.66 MB read + 3.37 MB written; save-mode launch: 5 396 B/row
-    # (786 432-row capture: 4.211 GB written + 0.032 GB read), scaled to this launch's rows.
+    step_ms = sum(ms_steps) / K
+    roofline_tensor = {"kernel": ("mlp_tc_kernel<fwd" + (", save" if args.workload == "train" else "") + "> (fused PE + 8x256 MLP + heads), fine pass")
+                       if args.precision == "bf16" else "fp32 check-mode SGEMM chain",
+                       "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                       "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + ", burst bf16 matmul",
+                       "frac_of_sustained": (achieved / pk["bf16_tflops_sustained"]) if pk.get("bf16_tflops_sustained") else None,
+                       "rows_per_launch": rows_max, "flop_per_row": FLOP_PER_ROW_FWD, "avg_launch_ms": avg_ms,
+                       "share_of_step": mlp_ms_per_step / step_ms, "traffic": None}
+    # DRAM traffic per launch from the committed ncu --set full captures (profiles/r01b_*_ncu_summary.csv), per row x rows
     if args.precision == "bf16":
         if args.workload == "render" and rows_max == 3145728:
-            roofline["traffic"] = 26.03e6
-            roofline["traffic_source"] = "ncu dram__bytes_read+write, profiles/r01_mlp_fwd_ncu_summary.csv"
+            roofline_tensor["traffic"] = NCU_BYTES_FWD_INFER_3145728
+            roofline_tensor["traffic_source"] = "ncu dram__bytes_read+write, profiles/r01b_mlp_fwd_ncu_summary.csv"
         elif args.workload == "train":
-            roofline["traffic"] = 5396.0 * rows_max
-            roofline["traffic_source"] = ("ncu dram__bytes_read+write per row (save-mode launch, 786 432-row capture, "
-                                          "profiles/r01_train_step_ncu_summary.csv) x rows of this launch")
-        else:
-            roofline["traffic"] = None
-    else:
-        roofline["traffic"] = None
+            roofline_tensor["traffic"] = NCU_BYTES_PER_ROW_FWD_SAVE * rows_max
+            roofline_tensor["traffic_source"] = ("ncu dram__bytes_read+write per row of the 196 608-row save-mode launch "
+                                                 "(profiles/r01b_train_step_ncu_summary.csv) x rows of this launch")
+    roofline = roofline_tensor
+    if stage_acc is not None and args.precision == "bf16" and "mlp_bwd_wgrad" in stage_acc:
+        wg_ms = stage_acc["mlp_bwd_wgrad"]
+        gbs = rows_max * WGRAD_ALG_BYTES_PER_ROW / (wg_ms * 1e-3) / 1e9
+        roofline = {"kernel": "wgrad_tc_kernel (split-K dW = dY^T X over sample rows, tcgen05, TMA-fed; + heads_wgrad beside it)",
+                    "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                    "peak_source": pk["source"] + ", copy bandwidth (read+write)",
+                    "rows_per_launch": rows_max, "bytes_per_row": WGRAD_ALG_BYTES_PER_ROW, "avg_launch_ms": wg_ms,
+                    "share_of_step": wg_ms / step_ms,
+                    "traffic": NCU_BYTES_PER_ROW_WGRAD * rows_max,
+                    "traffic_source": "ncu dram__bytes_read+write per row (profiles/r01b_train_step_ncu_summary.csv) x rows"}
 
     line = {"metric": f"{args.workload}_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload == "train" else "strong",
@@ -394,6 +412,8 @@ def main():
             "wall_s_timed_region": wall, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roofline}
+    if roofline is not roofline_tensor:
+        line["roofline_tensor"] = roofline_tensor
 
     if stage_acc is not None:
         line["stage_ms"] = {k_: round(v_, 5) for k_, v_ in stage_acc.items()}

@@ -89,6 +89,17 @@ int nerf_mlp_fwd_encoded(const float* x_enc, const float* d_enc, int64_t M, cons
 int nerf_mlp_bwd(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
                  float* flat_grads, void* workspace, size_t workspace_bytes, int precision,
                  void* stream);
+/* The same backward, one stage at a time (for per-stage timing / scheduling by the caller):
+ * NERF_BWD_DGRAD writes d(pre-activation) of every layer into the workspace, NERF_BWD_WGRAD
+ * accumulates the weight / bias gradients from it; NERF_BWD_ALL = both = nerf_mlp_bwd.
+ * (fp32 check mode has a single fused backward: it runs on NERF_BWD_DGRAD | NERF_BWD_ALL and
+ * NERF_BWD_WGRAD is a no-op.) */
+#define NERF_BWD_ALL   0
+#define NERF_BWD_DGRAD 1
+#define NERF_BWD_WGRAD 2
+int nerf_mlp_bwd_stage(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
+                       float* flat_grads, void* workspace, size_t workspace_bytes, int precision, int stage,
+                       void* stream);
 
 /* Volume rendering integral, NeRFRenderer._raw2outputs (renderer.py:114-163).
  * noise[R,S] nullable (already scaled by raw_noise_std, :134-136); weights[R,S] nullable. */

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("NERF_B200_LIB") or os.path.join(_HERE, "csrc", "libne
 N_PARAMS = 595844
 PREC_BF16, PREC_FP32 = 0, 1
 TRAIN_STATE_DOUBLES = 96
+BWD_ALL, BWD_DGRAD, BWD_WGRAD = 0, 1, 2
 
 _P = c_void_p
 # name -> (restype, argtypes); mirrors include/nerf_b200.h line by line
@@ -34,6 +35,7 @@ SIGNATURES = {
     "nerf_mlp_fwd_rays": (c_int, [_P, _P, _P, c_int, c_int, c_float, _P, _P, _P, _P, c_size_t, c_int, c_int, _P]),
     "nerf_mlp_fwd_encoded": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_size_t, c_int, c_int, _P]),
     "nerf_mlp_bwd": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_size_t, c_int, _P]),
+    "nerf_mlp_bwd_stage": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_size_t, c_int, c_int, _P]),
     "nerf_composite_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "nerf_composite_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "nerf_sample_pdf": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),

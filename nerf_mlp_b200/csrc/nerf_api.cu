@@ -90,14 +90,25 @@ extern "C" int nerf_mlp_fwd_encoded(const float* x_enc, const float* d_enc, int6
                         workspace, workspace_bytes, save, (cudaStream_t)stream);
 }
 
-extern "C" int nerf_mlp_bwd(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
-                            float* flat_grads, void* workspace, size_t workspace_bytes, int precision,
-                            void* stream) {
+extern "C" int nerf_mlp_bwd_stage(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
+                                  float* flat_grads, void* workspace, size_t workspace_bytes, int precision, int stage,
+                                  void* stream) {
   NERF_CHECK_ARG(M >= 0, "nerf_mlp_bwd: bad M=%lld", (long long)M);
+  NERF_CHECK_ARG(stage == NERF_BWD_ALL || stage == NERF_BWD_DGRAD || stage == NERF_BWD_WGRAD, "nerf_mlp_bwd: unknown stage %d", stage);
   if (check_prec(precision, packed, "nerf_mlp_bwd")) return -1;
   if (M == 0) return 0;
   NERF_CHECK_ARG(d_raw && params && flat_grads && workspace, "nerf_mlp_bwd: null pointer");
-  if (precision == NERF_PREC_FP32)
+  if (precision == NERF_PREC_FP32) {
+    if (stage == NERF_BWD_WGRAD) return 0;
     return mlp_fp32_backward(d_raw, M, params, flat_grads, (float*)workspace, workspace_bytes, (cudaStream_t)stream);
-  return mlp_tc_backward(d_raw, M, rows_per_dir, params, packed, flat_grads, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
+  return mlp_tc_backward(d_raw, M, rows_per_dir, params, packed, flat_grads, workspace, workspace_bytes, stage,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int nerf_mlp_bwd(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
+                            float* flat_grads, void* workspace, size_t workspace_bytes, int precision,
+                            void* stream) {
+  return nerf_mlp_bwd_stage(d_raw, M, rows_per_dir, params, packed, flat_grads, workspace, workspace_bytes, precision,
+                            NERF_BWD_ALL, stream);
 }

@@ -81,6 +81,6 @@ int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals
                    const float* params, const void* packed, float* out, void* ws, size_t ws_bytes,
                    int save, cudaStream_t st);
 int mlp_tc_backward(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
-                    float* grads, void* ws, size_t ws_bytes, cudaStream_t st);
+                    float* grads, void* ws, size_t ws_bytes, int stage, cudaStream_t st);
 
 }  // namespace nerf

@@ -60,6 +60,14 @@ constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 8;
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 
+#ifdef NERF_DBG_TIMING
+__device__ unsigned long long g_dbg_clk[8];
+#define DBG_T(var) const long long var = clock64()
+#define DBG_ACC(i, v) do { if (blockIdx.x == 0 && warp == kFirstComputeWarp && lane == 0) g_dbg_clk[i] += (unsigned long long)(v); } while (0)
+#else
+#define DBG_T(var)
+#define DBG_ACC(i, v)
+#endif
 __constant__ Slot c_slots[kMaxSlots];          // forward schedule, then the dgrad schedule
 __constant__ PackSlot c_pack[kMaxSlots];
 __constant__ int c_nslots_fwd, c_nslots_bwd;
@@ -424,12 +432,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
         for (int i = 0; i < nslots; ++i) {
           const uint4 rec = *reinterpret_cast<const uint4*>(&c_slots[slot0 + i]);
           const uint32_t a_add = rec.z, fl = rec.w;
+#ifdef NERF_DBG_TIMING
+          const long long i0_ = clock64();
+#endif
           mbar_wait(bar_full(s), ph, 200 + (int)s);
           // plain (cta-scope) waits, as CUTLASS's 2-SM pipelines do: the remote arrivals are
           // release.cluster and the data they publish is consumed by the async proxy (the MMA)
           if (kCtas == 2) mbar_wait(bar_pfull(s), ph, 220 + (int)s);
+#ifdef NERF_DBG_TIMING
+          const long long i1_ = clock64();
+#endif
           if (fl & kFlagFirst) { mbar_wait(bar_act(t), act_ph, 300 + t); act_ph ^= 1; }
           tc_fence_after();
+#ifdef NERF_DBG_TIMING
+          if (blockIdx.x == 0 && warp == 1 && lane == 0) {
+            g_dbg_clk[4] += (unsigned long long)(i1_ - i0_);
+            g_dbg_clk[5] += (unsigned long long)(clock64() - i1_);
+            g_dbg_clk[6] += 1;
+          }
+#endif
           const uint32_t kind = fl & 3u;
           const uint32_t a_lo = (kind == A_X ? a_lo_x : (kind == A_ACT ? a_lo_act : a_lo_ones)) + a_add;
           const uint32_t a_hi = (kind == A_ONES) ? kHiOnes : kHiSw128;
@@ -529,9 +550,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             const bool valid = row < a.M;
             uint8_t* at = smem + kOffAct + t * kActBytes;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256;
+            DBG_T(t0_);
             mbar_wait(bar_acc(t), (acc_ph >> t) & 1u, 400 + t);
             acc_ph ^= 1u << t;
             tc_fence_after();
+            DBG_T(t1_);
+            DBG_ACC(0, t1_ - t0_);
             if (g < 9) {
 #pragma unroll 1
              for (int ch = ch_lo; ch < ch_hi; ++ch) {
@@ -582,11 +606,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
               tc_fence_before();
               fence_proxy_async();
               act_arrive(t);
+              DBG_T(t2_);
+              DBG_ACC(1, t2_ - t1_);
+              DBG_ACC(3, 1);
               if (g == 7) { if (t) sigma1 = sigma; else sigma0 = sigma; }
               if (kSave) {                                 // off the critical path: the MMAs are already released
 #pragma unroll 1
                 for (int ch = ch_lo; ch < ch_hi; ++ch)
                   store_blocks(a.act_img + ((int64_t)g * ntiles + tile) * 65536, 2 * ch, at, 2 * ch, 2);
+                DBG_T(t3_);
+                DBG_ACC(2, t3_ - t2_);
               }
             } else {
               // view layer epilogue: + view bias, ReLU (model.py:73-74), rgb head (:75), output [rgb, sigma] (:77)
@@ -731,9 +760,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
               m0 = __ldg(mp + ch_lo);
               if (!kShared) m1 = __ldg(mp + 1);
             }
+            DBG_T(t0_);
             mbar_wait(bar_acc(t), (acc_ph >> t) & 1u, 400 + t);
             acc_ph ^= 1u << t;
             tc_fence_after();
+            DBG_T(t1_);
+            DBG_ACC(0, t1_ - t0_);
             // one 32-column chunk: (+ sigma term) -> ReLU mask -> bf16 -> swizzled store
             auto bchunk = [&](const uint32_t (&r)[32], int c0, uint32_t mw, bool with_sigma) {
               float v[32];
@@ -775,14 +807,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             tc_fence_before();
             fence_proxy_async();
             if (g < kNumGemms - 1) act_arrive(t);
+            DBG_T(t2_);
+            DBG_ACC(1, t2_ - t1_);
+            DBG_ACC(3, 1);
 #pragma unroll 1
             for (int ch = ch_lo; ch < ch_hi; ++ch)
               store_blocks(a.dpre_img + ((int64_t)dst * ntiles + tile) * 65536, 2 * ch, at, 2 * ch, 2);
+            DBG_T(t3_);
+            DBG_ACC(2, t3_ - t2_);
           }
         }
       }
     }
   }
+#ifdef NERF_DBG_TIMING
+  if (blockIdx.x == 0 && warp == kFirstComputeWarp && lane == 0 && g_dbg_clk[3] > 0) {
+    const double n = (double)g_dbg_clk[3];
+    printf("DBG kBwd=%d kSave=%d kCtas=%d: per tile-layer epilogue (warp 3, CTA 0): wait_acc %.0f clk, critical %.0f clk, copy-out %.0f clk, n=%.0f\n",
+           (int)kBwd, (int)kSave, kCtas, g_dbg_clk[0] / n, g_dbg_clk[1] / n, g_dbg_clk[2] / n, n);
+    printf("DBG issuer A (CTA 0): per slot: weight wait %.0f clk, activation wait %.0f clk (x slots per layer ~8.7), slots=%.0f\n",
+           g_dbg_clk[4] / (double)g_dbg_clk[6], g_dbg_clk[5] / (double)g_dbg_clk[6], (double)g_dbg_clk[6]);
+    g_dbg_clk[0] = g_dbg_clk[1] = g_dbg_clk[2] = g_dbg_clk[3] = g_dbg_clk[4] = g_dbg_clk[5] = g_dbg_clk[6] = 0;
+  }
+#endif
   __syncthreads();
   if (kCtas == 2) cluster_sync();                     // the peer may still be signalling this CTA's barriers
   if (warp == 1) {
@@ -869,7 +916,7 @@ int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals
 }
 
 int mlp_tc_backward(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
-                    float* grads, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    float* grads, void* ws, size_t ws_bytes, int stage, cudaStream_t st) {
   const WsLayout L = ws_layout(M, 1);
   NERF_CHECK_ARG(ws_bytes >= L.total, "mlp tc backward: workspace too small (%zu < %zu)", ws_bytes, L.total);
   NERF_CHECK_ARG(rows_per_dir >= 1, "mlp tc backward: rows_per_dir must be >= 1");
@@ -880,7 +927,8 @@ int mlp_tc_backward(const float* d_raw, int64_t M, int rows_per_dir, const float
   a.d_raw = d_raw; a.M = M; a.packed = (const uint8_t*)packed; a.params = params;
   fill_saved(a, ws, L);
   a.num_pairs = ceil_div(M, 2 * kTileM);
-  if ((rc = launch_tc<true, false>(a, st))) return rc;                       // d(pre-activations) -> workspace
+  if (stage != NERF_BWD_WGRAD && (rc = launch_tc<true, false>(a, st))) return rc;     // d(pre-activations) -> workspace
+  if (stage == NERF_BWD_DGRAD) return 0;
   return mlp_tc_wgrad(ws, L, d_raw, M, rows_per_dir, grads, st);            // weight / bias gradients
 }
 

@@ -158,12 +158,14 @@ def mlp_fwd_encoded(model, x_enc, d_enc, precision, save):
     return out, (ws if save else None)
 
 
-def mlp_bwd(model, d_raw, ws, precision, flat_grads, rows_per_dir):
+def mlp_bwd(model, d_raw, ws, precision, flat_grads, rows_per_dir, stage=_lib.BWD_ALL):
+    """stage: BWD_ALL (default) | BWD_DGRAD | BWD_WGRAD -- see include/nerf_b200.h nerf_mlp_bwd_stage."""
     _lib.require_cuda(d_raw, flat_grads)
     M = d_raw.numel() // 4
     packed = model.packed_weights() if precision == PREC_BF16 else None
-    check(dll().nerf_mlp_bwd(ptr(d_raw), M, int(rows_per_dir), ptr(model.flat_params), ptr(packed), ptr(flat_grads),
-                             ptr(ws), ws.numel(), int(precision), stream_ptr(d_raw.device)), "nerf_mlp_bwd")
+    check(dll().nerf_mlp_bwd_stage(ptr(d_raw), M, int(rows_per_dir), ptr(model.flat_params), ptr(packed), ptr(flat_grads),
+                                   ptr(ws), ws.numel(), int(precision), int(stage), stream_ptr(d_raw.device)),
+          "nerf_mlp_bwd")
 
 
 def _untile(img, rows, feats):

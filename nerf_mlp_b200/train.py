@@ -150,8 +150,13 @@ class TrainStep:
         d_raw = ops.composite_bwd(raw1, z_fine, d, noise1, white, d_rgb)
         m._flat_grad.zero_()                                                 # optimizer.zero_grad()
         self._mark("composite_fwd_fine+mse+composite_bwd")
-        ops.mlp_bwd(m, d_raw, ws, prec, m._flat_grad, z_fine.shape[1])
-        self._mark("mlp_bwd(dgrad+wgrad)")
+        if self.stage_events:                                                # same launches, one mark in between
+            ops.mlp_bwd(m, d_raw, ws, prec, m._flat_grad, z_fine.shape[1], _lib.BWD_DGRAD)
+            self._mark("mlp_bwd_dgrad")
+            ops.mlp_bwd(m, d_raw, ws, prec, m._flat_grad, z_fine.shape[1], _lib.BWD_WGRAD)
+            self._mark("mlp_bwd_wgrad")
+        else:
+            ops.mlp_bwd(m, d_raw, ws, prec, m._flat_grad, z_fine.shape[1])
         self.outputs = {"rgb_map": rgb, "depth_map": depth, "acc_map": acc,
                         "rgb_map_coarse": rgb0, "depth_map_coarse": depth0, "acc_map_coarse": acc0}
         return (t_rand, z, noise0, raw0, w0, u, z_fine, noise1, raw1, ws, d_rgb, d_raw)
