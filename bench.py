@@ -35,9 +35,9 @@ FLOP_PER_ROW_BWD = 2302208
 # layers + d_bottleneck (9 x 512 B) + d_hv (256 B); X = h0..h7 + bottleneck (9 x 512 B) + x_enc (128 B) + dir_enc (128 B)
 WGRAD_ALG_BYTES_PER_ROW = 9 * 512 + 256 + 9 * 512 + 128 + 128
 # measured DRAM traffic (ncu dram__bytes_read.sum + dram__bytes_write.sum), see profiles/
-NCU_BYTES_PER_ROW_FWD_SAVE = 5164.0      # 1.0153 GB on the 196 608-row save-mode launch
-NCU_BYTES_PER_ROW_WGRAD = 10548.0        # 2.0740 GB on the same rows
-NCU_BYTES_FWD_INFER_3145728 = 26.03e6    # whole 3 145 728-row inference launch
+NCU_BYTES_PER_ROW_FWD_SAVE = 5146.0      # 1.0117 GB on the 196 608-row save-mode launch
+NCU_BYTES_PER_ROW_WGRAD = 10544.0        # 2.0730 GB on the same rows
+NCU_BYTES_FWD_INFER_3145728 = 25.27e6    # whole 3 145 728-row inference launch (22.67 MB read + 2.60 MB written)
 N_SAMPLES, N_IMPORTANCE = 64, 128
 
 
