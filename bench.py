@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (train) / total rays (render)")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--samples", type=int, default=64, help="coarse samples per ray (BASELINE configs[4] stress: 256)")
+    ap.add_argument("--importance", type=int, default=128, help="importance samples per ray (stress: 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="train: enqueue the step eagerly instead of replaying the CUDA graph")
     ap.add_argument("--autograd", action="store_true", help="train: the reference's loop on the drop-in classes (autograd + FlatAdam)")
@@ -198,7 +200,9 @@ def workload_config(args, rays_override=None):
 
 # ------------------------------------------------------------------------------------------------
 def main():
+    global N_SAMPLES, N_IMPORTANCE
     args = parse()
+    N_SAMPLES, N_IMPORTANCE = args.samples, args.importance
     if args.impl == "reference":
         return run_reference(args)
 
@@ -387,7 +391,7 @@ def main():
     # DRAM traffic per launch from the committed ncu --set full captures (profiles/r01b_*_ncu_summary.csv), per row x rows
     if args.precision == "bf16":
         if args.workload == "render" and rows_max == 3145728:
-            roofline_tensor["traffic"] = NCU_BYTES_FWD_INFER_3145728
+            roofline_tensor["traffic"] = NCU_BYTES_FWD_INFER_3145728 if (N_SAMPLES, N_IMPORTANCE) == (64, 128) else None
             roofline_tensor["traffic_source"] = "ncu dram__bytes_read+write, profiles/r01b_mlp_fwd_ncu_summary.csv"
         elif args.workload == "train":
             roofline_tensor["traffic"] = NCU_BYTES_PER_ROW_FWD_SAVE * rows_max

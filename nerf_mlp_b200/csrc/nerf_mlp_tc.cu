@@ -47,9 +47,15 @@ constexpr int kNumGemmsFwd = 10, kNumGemmsBwd = 9;
 // ---- shared memory map (bytes) ------------------------------------------------------------------
 constexpr int kOffAct = 0;                                   // 2 x [128 x 256] bf16, SW128 K-blocks of 64
 constexpr int kActBytes = 65536;
+#ifdef NERF_DBG_ALIAS_X   // timing experiment only (wrong results): x-tiles alias the activation tiles, ring takes their 32 KB
+constexpr int kOffX = kOffAct;
+constexpr int kXBytes = kActBytes;
+constexpr int kOffRing = kOffAct + 2 * kActBytes;
+#else
 constexpr int kOffX = kOffAct + 2 * kActBytes;               // 2 x [128 x 64] bf16, SW128
 constexpr int kXBytes = 16384;
 constexpr int kOffRing = kOffX + 2 * kXBytes;
+#endif
 constexpr int kOffOnes = kOffRing + kRing * kSlotBytes;      // [8 x 16] bf16, SW32; all 16 row groups alias it (SBO = 0)
 constexpr int kOnesBytes = 256;
 constexpr int kOffHead = kOffOnes + kOnesBytes;              // w_sigma[256] w_rgb[3][128] b_sigma b_rgb[3]
