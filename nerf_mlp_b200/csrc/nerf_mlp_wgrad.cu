@@ -77,8 +77,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const WgradJob& job = jobs.j[ji];
   const int slab = blockIdx.x - job.first_block;
   const int64_t total_chunks = Mp / kWgChunkRows;
-  const int64_t c_beg = total_chunks * slab / job.nslabs, c_end = total_chunks * (slab + 1) / job.nslabs;
-  const int nchunks = (int)(c_end - c_beg);
+  // Slab s takes the 64-row chunks  total-1-s, total-1-s-nslabs, ...  (interleaved, descending): the
+  // dgrad kernel wrote the highest tiles last, so every CTA starts on dY data that is still in L2.
+  const int nchunks = slab < total_chunks ? (int)((total_chunks - 1 - slab) / job.nslabs) + 1 : 0;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1 + kWgBiasWarps); }
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % kWgStages;
         if (c >= kWgStages) mbar_wait(bar_empty(s), ((c / kWgStages) - 1) & 1, 600 + s);
-        const int64_t chunk = c_beg + c;
+        const int64_t chunk = total_chunks - 1 - slab - (int64_t)c * job.nslabs;
         const int64_t tile = chunk >> 1;
         const uint32_t half = (uint32_t)(chunk & 1) * 8192u;      // rows 0-63 / 64-127 of the tile
         const uint32_t sa = sbase + s * kWgStageBytes, sb = sa + kWgOffB;
