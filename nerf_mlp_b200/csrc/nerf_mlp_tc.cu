@@ -917,7 +917,7 @@ int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals
   a.vb = vb; a.vb_div = (x_enc != nullptr) ? 1 : S;
   a.out = out;
   if (save) fill_saved(a, ws, L);
-  a.num_pairs = ceil_div(M, 2 * kTileM);
+  a.num_pairs = (int)(L.Mp / (2 * kTileM));   // the whole padded tile range: every tile image the wgrad kernel reads is written (single-CTA mode too)
   return save ? launch_tc<false, true>(a, st) : launch_tc<false, false>(a, st);
 }
 
@@ -932,7 +932,7 @@ int mlp_tc_backward(const float* d_raw, int64_t M, int rows_per_dir, const float
   TcArgs a{};
   a.d_raw = d_raw; a.M = M; a.packed = (const uint8_t*)packed; a.params = params;
   fill_saved(a, ws, L);
-  a.num_pairs = ceil_div(M, 2 * kTileM);
+  a.num_pairs = (int)(L.Mp / (2 * kTileM));   // the whole padded tile range: every tile image the wgrad kernel reads is written (single-CTA mode too)
   if (stage != NERF_BWD_WGRAD && (rc = launch_tc<true, false>(a, st))) return rc;     // d(pre-activations) -> workspace
   if (stage == NERF_BWD_DGRAD) return 0;
   return mlp_tc_wgrad(ws, L, d_raw, M, rows_per_dir, grads, st);            // weight / bias gradients
