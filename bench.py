@@ -26,8 +26,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner with printf)
+# get stderr as their fd 1 for the whole run; emit() writes the result line to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 FLOP_PER_ROW_FWD = 1186816          # un-padded MACs x 2
 FLOP_PER_ROW_BWD = 2302208
@@ -179,7 +186,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
                              "sample": f"{rays}-ray {args.workload} step, 64+128 samples, numpy/OpenBLAS fp32, median of {steps}"},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, rays_override=None):
@@ -431,7 +438,7 @@ def main():
         line["cpu_baseline"] = {"value": rays_cpu / sec, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{rays_cpu}-ray {args.workload} step, 64+128 samples, numpy/OpenBLAS fp32 oracle port, median of 3"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         td.destroy_process_group()
 
