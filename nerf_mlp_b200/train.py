@@ -48,7 +48,7 @@ class TrainStep:
     (one D2H copy + sync, for the periodic logging the reference does every step).
     """
 
-    def __init__(self, renderer, optimizer, n_rays, *, graph=True, warmup=2, stage_events=False):
+    def __init__(self, renderer, optimizer, n_rays, *, graph=True, warmup=2, stage_events=False, split_graphs=None):
         self.renderer, self.opt, self.model = renderer, optimizer, renderer.model
         if torch.device(renderer.device).type != "cuda":
             raise RuntimeError("nerf_mlp_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -83,6 +83,9 @@ class TrainStep:
         self._ptrs = None
         # optional device timeline: one (external, graph-capturable) CUDA event after every stage
         self.stage_events = bool(stage_events)
+        # two graphs (forward+backward | metrics+Adam+repack) with the eager all-reduce between them: always
+        # at world_size > 1; split_graphs=True forces the same structure on one GPU (tests)
+        self.split_graphs = split_graphs
         self._marks = []
         self._push_state(force=True)
         if self.use_graph:
@@ -215,7 +218,8 @@ class TrainStep:
         pool = None
         launches0 = dll().nerf_launch_count()
         with torch.no_grad():
-            parts = [(self._fwd_bwd, self._update)] if self._world() == 1 else [(self._fwd_bwd,), (self._update,)]
+            split = self._world() > 1 if self.split_graphs is None else (self.split_graphs or self._world() > 1)
+            parts = [(self._fwd_bwd,), (self._update,)] if split else [(self._fwd_bwd, self._update)]
             for fns in parts:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=pool):

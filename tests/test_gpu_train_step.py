@@ -173,6 +173,38 @@ def test_external_weight_load_is_seen_by_the_graph(nb):
     assert l1 == ref and l1 != l0
 
 
+def test_data_parallel_graph_structure(nb):
+    """The world_size > 1 structure (two graphs with the gradient exchange between them, 1/world folded
+    into the Adam kernel) on one GPU: identical to the single-graph step (bit-identical loss, same bars
+    on the parameters); with world_size forced to 2 and the all-reduce stubbed by a doubling (two ranks
+    with the same batch), Adam sees the same averaged gradient."""
+    R = 96
+    o, d, tgt = batch(R, 41)
+    out = {}
+    for kind in ("single", "split", "world2"):
+        m, r, opt = make(nb, 11, "bf16", 0.0)
+        cls = nb.TrainStep
+        if kind == "world2":
+            opt._world = 2
+
+            class TwoIdenticalRanks(nb.TrainStep):
+                def _allreduce(self):                               # sum over two ranks holding the same batch
+                    self.model._flat_grad.mul_(2.0)
+            cls = TwoIdenticalRanks
+        step = cls(r, opt, R, split_graphs=(kind != "single"))
+        if kind == "world2":
+            assert float(step.state[4]) == 0.5
+        losses = [float(step(o, d, tgt)) for _ in range(3)]
+        assert len(step._graphs) == (1 if kind == "single" else 2)
+        out[kind] = (losses, m.flat_params.detach().cpu().numpy().copy(), step.read_metrics()["grad_norm"])
+    for kind in ("split", "world2"):
+        assert out[kind][0][0] == out["single"][0][0]
+        np.testing.assert_allclose(out[kind][0], out["single"][0], rtol=2e-4)
+        np.testing.assert_allclose(out[kind][1], out["single"][1], atol=2.1e-3)
+        assert np.mean(np.abs(out[kind][1] - out["single"][1]) <= 2e-5) > 0.85
+        assert abs(out[kind][2] - out["single"][2]) <= 1e-3 * out["single"][2]
+
+
 def test_shape_and_config_errors(nb):
     m, r, opt = make(nb, 3, "bf16", 1.0)
     step = nb.TrainStep(r, opt, 32, graph=False)
