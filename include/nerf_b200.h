@@ -63,7 +63,19 @@ int nerf_positional_encoding(const float* x, int64_t n, int d, const float* freq
 int nerf_stratified_z(const float* t_vals, const float* t_rand, int R, int S, float near_, float far_,
                       float* z_vals, void* stream);
 
-/* Workspace size for the MLP kernels: M sample rows, `save` = keep activations for backward. */
+/* `save` argument of the MLP forwards:
+ *   0                     inference
+ *   1                     keep the activations the backward needs in the workspace
+ *   NERF_FWD_DENSITY_ONLY inference that stops after layer 7 + sigma_linear: raw[...,3] (sigma) is the
+ *                         reference's value, raw[...,0:3] = 0.  For the COARSE pass of render() and of a
+ *                         training step, whose only consumer is the hierarchical resampling
+ *                         (renderer.py:79-87 reads `weights`, a function of sigma alone; the coarse colour maps
+ *                         are dropped at renderer.py:44 and never reach the loss, scripts/train.py:374-376):
+ *                         skips bottleneck_linear, view_linear and rgb_linear (17 % of the pass).
+ *                         (fp32 check mode evaluates the whole network in every mode.) */
+#define NERF_FWD_DENSITY_ONLY 2
+
+/* Workspace size for the MLP kernels: M sample rows, `save` as above. */
 size_t nerf_mlp_workspace_bytes(int64_t M, int precision, int save);
 
 /* MLP forward from rays: points o + d*z (renderer.py:63), *coord_scale (:67-68), positional

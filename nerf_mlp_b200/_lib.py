@@ -19,6 +19,7 @@ N_PARAMS = 595844
 PREC_BF16, PREC_FP32 = 0, 1
 TRAIN_STATE_DOUBLES = 96
 BWD_ALL, BWD_DGRAD, BWD_WGRAD = 0, 1, 2
+FWD_DENSITY_ONLY = 2
 
 _P = c_void_p
 # name -> (restype, argtypes); mirrors include/nerf_b200.h line by line

@@ -48,6 +48,7 @@ extern "C" int nerf_pack_weights(const float* flat_params, void* packed, void* s
 
 extern "C" size_t nerf_mlp_workspace_bytes(int64_t M, int precision, int save) {
   if (M <= 0) return 0;
+  if (save == NERF_FWD_DENSITY_ONLY) save = 0;
   if (precision == NERF_PREC_FP32) {
     const int64_t rows = save ? M : (M < 262144 ? M : 262144);
     return (size_t)rows * mlp_fp32_workspace_floats_per_row(save) * sizeof(float);
@@ -68,10 +69,11 @@ extern "C" int nerf_mlp_fwd_rays(const float* rays_o, const float* rays_d, const
   if (check_prec(precision, packed, "nerf_mlp_fwd_rays")) return -1;
   if (R == 0) return 0;
   NERF_CHECK_ARG(rays_o && rays_d && z_vals && params && raw, "nerf_mlp_fwd_rays: null pointer");
+  NERF_CHECK_ARG(save >= 0 && save <= 2, "nerf_mlp_fwd_rays: save must be 0, 1 or NERF_FWD_DENSITY_ONLY (got %d)", save);
   const int64_t M = (int64_t)R * S;
-  if (precision == NERF_PREC_FP32)
+  if (precision == NERF_PREC_FP32)     // check mode evaluates the whole network in every mode
     return mlp_fp32_forward(rays_o, rays_d, z_vals, R, S, coord_scale, nullptr, nullptr, M, params, raw,
-                            (float*)workspace, workspace_bytes, save, (cudaStream_t)stream);
+                            (float*)workspace, workspace_bytes, save == 1, (cudaStream_t)stream);
   return mlp_tc_forward(rays_o, rays_d, z_vals, R, S, coord_scale, nullptr, nullptr, M, params, packed, raw,
                         workspace, workspace_bytes, save, (cudaStream_t)stream);
 }
@@ -83,6 +85,7 @@ extern "C" int nerf_mlp_fwd_encoded(const float* x_enc, const float* d_enc, int6
   if (check_prec(precision, packed, "nerf_mlp_fwd_encoded")) return -1;
   if (M == 0) return 0;
   NERF_CHECK_ARG(x_enc && d_enc && params && out, "nerf_mlp_fwd_encoded: null pointer");
+  NERF_CHECK_ARG(save == 0 || save == 1, "nerf_mlp_fwd_encoded: save must be 0 or 1 (got %d)", save);
   if (precision == NERF_PREC_FP32)
     return mlp_fp32_forward(nullptr, nullptr, nullptr, 0, 1, 1.f, x_enc, d_enc, M, params, out,
                             (float*)workspace, workspace_bytes, save, (cudaStream_t)stream);

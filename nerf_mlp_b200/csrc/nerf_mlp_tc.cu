@@ -76,12 +76,13 @@ __device__ unsigned long long g_dbg_clk[8];
 #endif
 __constant__ Slot c_slots[kMaxSlots];          // forward schedule, then the dgrad schedule
 __constant__ PackSlot c_pack[kMaxSlots];
-__constant__ int c_nslots_fwd, c_nslots_bwd;
+__constant__ int c_nslots_fwd, c_nslots_bwd, c_nslots_fwd_sigma;
 
 struct Schedule {
   std::vector<Slot> slots;
   std::vector<PackSlot> pack;
   int n_fwd = 0, n_bwd = 0;
+  int n_fwd_sigma = 0;             // forward slots through layer 7 (density-only forward: sigma head, no view branch)
   size_t bytes = 0;
 };
 
@@ -110,6 +111,7 @@ static const Schedule& schedule() {
       bwd.push_back({256, -1, {{A_ACT, 256, W(l) + (l == 5 ? 63 : 0), 1, kIn[l], 256}}});
     uint32_t goff = 0;
     auto emit = [&](const std::vector<G>& gs) {
+      int gi = 0;
       for (const G& g : gs) {
         const size_t first_idx = s.slots.size();
         for (const Part& p : g.parts) {
@@ -138,6 +140,7 @@ static const Schedule& schedule() {
         }
         s.slots[first_idx].flags |= kFlagFirst;
         s.slots.back().flags |= kFlagLast;
+        if (&gs == &fwd && ++gi == 8) s.n_fwd_sigma = (int)s.slots.size();
       }
     };
     emit(fwd);
@@ -163,6 +166,7 @@ static int upload_schedule() {
   NERF_CUDA(cudaMemcpyToSymbol(c_pack, s.pack.data(), n * sizeof(PackSlot)));
   NERF_CUDA(cudaMemcpyToSymbol(c_nslots_fwd, &s.n_fwd, sizeof(int)));
   NERF_CUDA(cudaMemcpyToSymbol(c_nslots_bwd, &s.n_bwd, sizeof(int)));
+  NERF_CUDA(cudaMemcpyToSymbol(c_nslots_fwd_sigma, &s.n_fwd_sigma, sizeof(int)));
   if (dev < 64) done[dev] = true;
   return 0;
 }
@@ -328,8 +332,13 @@ __device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&r)[32]) {
 }
 
 // kBwd = false: forward (kSave: also write the tensors the backward needs); kBwd = true: dgrad chain
-template <bool kBwd, bool kSave, int kCtas>
+// kSigmaOnly (inference forward only): stop after layer 7 and the sigma head -- the coarse pass of a
+// render / training step only feeds the hierarchical resampling, which needs the density alone
+// (renderer.py:79-87 uses `weights`; the coarse colour maps are dropped by render(), renderer.py:44,
+// and never reach the loss, scripts/train.py:374-376).  Output rows are (0, 0, 0, sigma).
+template <bool kBwd, bool kSave, int kCtas, bool kSigmaOnly = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
+  static_assert(!kSigmaOnly || (!kBwd && !kSave), "density-only mode is an inference-forward mode");
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr bool kShared = !kBwd && !kSave;             // all eight compute warps share every epilogue
   constexpr int kRingK = kRing * kCtas;                 // ring slots per CTA (same bytes, half-size slots in pair mode)
@@ -351,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   const uint32_t bar_skew = bar0 + 8u * (kB0 + 4);                         // one-shot: tile A's issuer is kSkew slots in
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* head = reinterpret_cast<float*>(smem + kOffHead);
-  constexpr int kNumGemms = kBwd ? kNumGemmsBwd : kNumGemmsFwd;
+  constexpr int kNumGemms = kBwd ? kNumGemmsBwd : (kSigmaOnly ? 8 : kNumGemmsFwd);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kRingK; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 2); mbar_init(bar_pfull(s), 1); }
@@ -385,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int slot0 = kBwd ? c_nslots_fwd : 0;
-  const int nslots = kBwd ? c_nslots_bwd : c_nslots_fwd;
+  const int nslots = kBwd ? c_nslots_bwd : (kSigmaOnly ? c_nslots_fwd_sigma : c_nslots_fwd);
 
   if (warp == 0) {
     // ================= weight producer =================
@@ -562,7 +571,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             tc_fence_after();
             DBG_T(t1_);
             DBG_ACC(0, t1_ - t0_);
-            if (g < 9) {
+            if (kSigmaOnly && g == 7) {
+              // density-only forward, last layer: sigma head straight from the fp32 accumulators; nothing is
+              // written back to the activation tile and no MMA follows (the next arrive is the next prologue's)
+#pragma unroll 1
+              for (int c0 = 128 * h; c0 < 128 * h + 128; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), head[c0 + j], sigma);
+              }
+              tc_fence_before();
+              if (h == 1) xchg[t * 32 + lane] = make_float4(0.f, 0.f, 0.f, sigma);
+              named_bar_sync(1, 256);
+              if (h == 0 && valid)
+                *reinterpret_cast<float4*>(a.out + row * 4) = make_float4(0.f, 0.f, 0.f, sigma + xchg[t * 32 + lane].w + head[640]);
+            } else if (g < 9) {
 #pragma unroll 1
              for (int ch = ch_lo; ch < ch_hi; ++ch) {
               uint32_t mkw[4];
@@ -854,7 +879,7 @@ static int num_ctas() {         // NERF_TC_CTAS_RT=1|2 overrides the compiled de
   }();
   return n;
 }
-template <bool kBwd, bool kSave, int kCtas>
+template <bool kBwd, bool kSave, int kCtas, bool kSigmaOnly = false>
 static int launch_tc_impl(const TcArgs& a, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
@@ -864,7 +889,7 @@ static int launch_tc_impl(const TcArgs& a, cudaStream_t st) {
     NERF_CUDA(cudaGetDeviceProperties(&p, dev));
     NERF_CHECK_ARG(p.major == 10, "libnerf_b200 needs an sm_100 device (found sm_%d%d); there is no fallback", p.major, p.minor);
     sm_count_cached = p.multiProcessorCount;
-    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<kBwd, kSave, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<kBwd, kSave, kCtas, kSigmaOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done = true;
   }
   const int units = (kCtas == 2) ? (a.num_pairs + 1) / 2 : a.num_pairs;
@@ -880,13 +905,13 @@ static int launch_tc_impl(const TcArgs& a, cudaStream_t st) {
   attr[0].val.clusterDim.x = kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (kCtas == 2) ? 1 : 0;
-  NERF_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<kBwd, kSave, kCtas>, a));
+  NERF_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<kBwd, kSave, kCtas, kSigmaOnly>, a));
   NERF_LAUNCH_CHECK(kBwd ? "mlp_tc_kernel<dgrad>" : "mlp_tc_kernel<fwd>");
   return 0;
 }
-template <bool kBwd, bool kSave>
+template <bool kBwd, bool kSave, bool kSigmaOnly = false>
 static int launch_tc(const TcArgs& a, cudaStream_t st) {
-  return num_ctas() == 2 ? launch_tc_impl<kBwd, kSave, 2>(a, st) : launch_tc_impl<kBwd, kSave, 1>(a, st);
+  return num_ctas() == 2 ? launch_tc_impl<kBwd, kSave, 2, kSigmaOnly>(a, st) : launch_tc_impl<kBwd, kSave, 1, kSigmaOnly>(a, st);
 }
 
 static void fill_saved(TcArgs& a, void* ws, const WsLayout& L) {
@@ -901,6 +926,8 @@ static void fill_saved(TcArgs& a, void* ws, const WsLayout& L) {
 int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float coord_scale,
                    const float* x_enc, const float* d_enc, int64_t M, const float* params, const void* packed,
                    float* out, void* ws, size_t ws_bytes, int save, cudaStream_t st) {
+  const bool sigma_only = (save == 2);                  // density-only inference forward (see mlp_tc_kernel)
+  if (sigma_only) save = 0;
   const WsLayout L = ws_layout(M, save);
   NERF_CHECK_ARG(ws_bytes >= L.total, "mlp tc forward: workspace too small (%zu < %zu)", ws_bytes, L.total);
   NERF_CHECK_ARG((((uintptr_t)packed | (uintptr_t)out | (uintptr_t)ws) & 15) == 0, "mlp tc forward: packed/out/workspace must be 16-byte aligned");
@@ -909,8 +936,10 @@ int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals
   float* vb = (float*)((uint8_t*)ws + L.vb);
   float* de = save ? (float*)((uint8_t*)ws + L.de) : nullptr;
   const int64_t nvb = (x_enc != nullptr) ? M : R;
-  view_bias_kernel<<<(unsigned)nvb, 128, 0, st>>>(rays_d, d_enc, nvb, params, vb, de);
-  NERF_LAUNCH_CHECK("view_bias_kernel");
+  if (!sigma_only) {                                    // the view branch is not evaluated in density-only mode
+    view_bias_kernel<<<(unsigned)nvb, 128, 0, st>>>(rays_d, d_enc, nvb, params, vb, de);
+    NERF_LAUNCH_CHECK("view_bias_kernel");
+  }
   TcArgs a{};
   a.rays_o = rays_o; a.rays_d = rays_d; a.z_vals = z_vals; a.S = S; a.coord_scale = coord_scale;
   a.x_enc = x_enc; a.M = M; a.packed = (const uint8_t*)packed; a.params = params;
@@ -918,6 +947,7 @@ int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals
   a.out = out;
   if (save) fill_saved(a, ws, L);
   a.num_pairs = (int)(L.Mp / (2 * kTileM));   // the whole padded tile range: every tile image the wgrad kernel reads is written (single-CTA mode too)
+  if (sigma_only) return launch_tc<false, false, true>(a, st);
   return save ? launch_tc<false, true>(a, st) : launch_tc<false, false>(a, st);
 }
 

@@ -134,15 +134,19 @@ def mlp_workspace(M, precision, save, device):
     return torch.empty(max(int(n), 16), device=device, dtype=torch.uint8)
 
 
-def mlp_fwd_rays(model, rays_o, rays_d, z_vals, coord_scale, precision, save):
+def mlp_fwd_rays(model, rays_o, rays_d, z_vals, coord_scale, precision, save, density_only=False):
+    """density_only (inference only): raw[..., 3] alone is computed (include/nerf_b200.h NERF_FWD_DENSITY_ONLY)."""
     _lib.require_cuda(rays_o, rays_d, z_vals)
+    if density_only and save:
+        raise RuntimeError("mlp_fwd_rays: density_only is an inference mode")
     R, S = z_vals.shape
     raw = _empty((R, S, 4), z_vals)
-    ws = mlp_workspace(R * S, precision, save, z_vals.device)
+    mode = _lib.FWD_DENSITY_ONLY if density_only else int(bool(save))
+    ws = mlp_workspace(R * S, precision, mode, z_vals.device)
     packed = model.packed_weights() if precision == PREC_BF16 else None
     check(dll().nerf_mlp_fwd_rays(ptr(rays_o), ptr(rays_d), ptr(z_vals), R, S, float(coord_scale),
                                   ptr(model.flat_params), ptr(packed), ptr(raw), ptr(ws), ws.numel(),
-                                  int(precision), int(bool(save)), stream_ptr(z_vals.device)), "nerf_mlp_fwd_rays")
+                                  int(precision), mode, stream_ptr(z_vals.device)), "nerf_mlp_fwd_rays")
     return raw, (ws if save else None)
 
 
@@ -234,7 +238,10 @@ class RenderPassFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, rays_o, rays_d, z_vals, noise, white_bkgd, coord_scale, precision, save, *params):
         # `save` is decided by the caller: grad mode is always off inside Function.forward
-        raw, ws = mlp_fwd_rays(model, rays_o, rays_d, z_vals, coord_scale, precision, save)
+        # save == "density": weights-only coarse pass (rgb/depth/acc maps of this pass are not meaningful)
+        density = isinstance(save, str) and save == "density"
+        raw, ws = mlp_fwd_rays(model, rays_o, rays_d, z_vals, coord_scale, precision, False if density else save,
+                               density_only=density)
         rgb, depth, acc, w = composite_fwd(raw, z_vals, rays_d, noise, white_bkgd, True)
         ctx.model, ctx.white, ctx.precision = model, white_bkgd, precision
         ctx.ws, ctx.noise = ws, noise

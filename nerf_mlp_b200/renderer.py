@@ -26,7 +26,7 @@ class NeRFRenderer:
                  pos_enc_L=10, dir_enc_L=4,
                  N_samples=64, N_importance=128,
                  near=2.0, far=6.0, white_bkgd=True, perturb=1.0, raw_noise_std=0.0, coord_scale=1.0,
-                 *, precision=None, coarse_grad=False):
+                 *, precision=None, coarse_grad=False, coarse_density_only=True):
         if not isinstance(model, NeRFMLP):
             raise TypeError("nerf_mlp_b200.NeRFRenderer needs a nerf_mlp_b200.NeRFMLP (the fused kernels "
                             "own the network; there is no generic nn.Module path)")
@@ -47,6 +47,9 @@ class NeRFRenderer:
         # extras (keyword-only, defaults keep the reference's behaviour)
         self.precision = precision            # None -> follow model.precision
         self.coarse_grad = coarse_grad        # reference training never back-props the coarse maps
+        # render() / TrainStep: evaluate the coarse pass for its densities only (its colour maps are dropped by
+        # render(), renderer.py:44, and unused by the loss); False = the whole network in both passes
+        self.coarse_density_only = coarse_density_only
         self._lin = {}
 
     # ---- helpers -------------------------------------------------------------------------------
@@ -62,7 +65,7 @@ class NeRFRenderer:
             self._lin[key] = t
         return t
 
-    def _pass(self, rays_o, rays_d, z_vals, want_grad):
+    def _pass(self, rays_o, rays_d, z_vals, want_grad, density_only=False):
         noise = None
         if self.raw_noise_std > 0.:
             noise = (torch.randn(z_vals.shape, device=z_vals.device) * self.raw_noise_std).contiguous()  # :134-136
@@ -72,7 +75,8 @@ class NeRFRenderer:
                                           float(self.coord_scale), self._prec(), True, *m._param_list)
         with torch.no_grad():
             return ops.RenderPassFn.apply(m, rays_o, rays_d, z_vals, noise, bool(self.white_bkgd),
-                                          float(self.coord_scale), self._prec(), False, *m._param_list)
+                                          float(self.coord_scale), self._prec(), "density" if density_only else False,
+                                          *m._param_list)
 
     # ---- reference API -------------------------------------------------------------------------
     def render(self, rays_o, rays_d, H, W, focal, chunk=1024 * 16):
@@ -82,7 +86,10 @@ class NeRFRenderer:
         results = []
         for i in range(0, N_rays, chunk):
             with torch.no_grad():
-                results.append(self._render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk])['rgb_map'])
+                # only the fine rgb_map leaves this function (renderer.py:44): the coarse pass is evaluated for
+                # its densities alone (same weights, hence bit-identical fine samples and fine maps)
+                results.append(self._render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk],
+                                                 _coarse_density_only=self.coarse_density_only)['rgb_map'])
         rgb_map = torch.cat(results, 0)
         return rgb_map.view(H, W, 3)
 
@@ -99,7 +106,10 @@ class NeRFRenderer:
             out[k] = v.view(H, W, 3) if v.dim() == 2 else v.view(H, W)
         return out
 
-    def _render_rays(self, rays_o, rays_d):
+    def _render_rays(self, rays_o, rays_d, _coarse_density_only=False):
+        """reference renderer.py:47-112.  `_coarse_density_only` (internal, used by render()): the coarse
+        colour/depth/acc maps are not needed by the caller, so the coarse pass computes densities only and
+        the returned dict has no *_coarse entries."""
         rays_o = _lib.f32c(rays_o)
         rays_d = _lib.f32c(rays_d)
         N_rays = rays_o.shape[0]
@@ -112,8 +122,9 @@ class NeRFRenderer:
             t_rand = torch.rand((N_rays, self.N_samples), device=self.device)                    # :60
         z_vals = ops.stratified_z(self._linspace(self.N_samples), t_rand, N_rays, self.near, self.far)
         fine = self.N_importance > 0
+        density_only = bool(_coarse_density_only) and fine and not grad
         rgb0, depth0, acc0, weights = self._pass(rays_o, rays_d, z_vals,
-                                                 grad and (self.coarse_grad or not fine))        # :63-80
+                                                 grad and (self.coarse_grad or not fine), density_only)  # :63-80
         if not fine:
             return {'rgb_map': rgb0, 'depth_map': depth0, 'acc_map': acc0}                       # :112
 
@@ -126,6 +137,8 @@ class NeRFRenderer:
 
         # === fine pass (renderer.py:91-107), same network ===
         rgb, depth, acc, _ = self._pass(rays_o, rays_d, z_fine, grad)
+        if density_only:
+            return {'rgb_map': rgb, 'depth_map': depth, 'acc_map': acc}
         return {'rgb_map': rgb, 'depth_map': depth, 'acc_map': acc,
                 'rgb_map_coarse': rgb0, 'depth_map_coarse': depth0, 'acc_map_coarse': acc0}
 

@@ -136,7 +136,10 @@ class TrainStep:
         z = ops.stratified_z(r._linspace(r.N_samples), t_rand, R, r.near, r.far)
         noise0 = (torch.randn(z.shape, device=self.dev) * r.raw_noise_std).contiguous() if r.raw_noise_std > 0. else None
         self._mark("stratified_z")
-        raw0, _ = ops.mlp_fwd_rays(m, o, d, z, cs, prec, False)
+        # the coarse pass only feeds the resampling: densities alone (NERF_FWD_DENSITY_ONLY) unless the
+        # renderer asks for the whole network (coarse_density_only=False)
+        dens = bool(r.coarse_density_only)
+        raw0, _ = ops.mlp_fwd_rays(m, o, d, z, cs, prec, False, density_only=dens)
         self._mark("mlp_fwd_coarse")
         rgb0, depth0, acc0, w0 = ops.composite_fwd(raw0, z, d, noise0, white, True)
         self._mark("composite_fwd_coarse")
@@ -160,8 +163,9 @@ class TrainStep:
             self._mark("mlp_bwd_wgrad")
         else:
             ops.mlp_bwd(m, d_raw, ws, prec, m._flat_grad, z_fine.shape[1])
-        self.outputs = {"rgb_map": rgb, "depth_map": depth, "acc_map": acc,
-                        "rgb_map_coarse": rgb0, "depth_map_coarse": depth0, "acc_map_coarse": acc0}
+        self.outputs = {"rgb_map": rgb, "depth_map": depth, "acc_map": acc}
+        if not dens:
+            self.outputs.update({"rgb_map_coarse": rgb0, "depth_map_coarse": depth0, "acc_map_coarse": acc0})
         return (t_rand, z, noise0, raw0, w0, u, z_fine, noise1, raw1, ws, d_rgb, d_raw)
 
     def _update(self):

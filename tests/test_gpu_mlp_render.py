@@ -399,3 +399,26 @@ def test_bf16_training_reduces_loss(nb):
     assert losses["bf16"][-1] < losses["bf16"][0] * 0.97
     assert losses["fp32"][-1] < losses["fp32"][0] * 0.97
     assert abs(losses["bf16"][-1] - losses["fp32"][-1]) < 0.05 * losses["fp32"][0]
+
+
+def test_density_only_coarse_pass(nb):
+    """NERF_FWD_DENSITY_ONLY (include/nerf_b200.h): sigma is bit-identical to the full forward's, the colour
+    channels are zero, and render() -- whose coarse pass runs in this mode -- returns bit-identical pixels to
+    the full _render_rays path (same weights -> same fine samples -> same fine maps)."""
+    m, p = make_model(nb, 3, "bf16")
+    R, S = 777, 64
+    o, d = O.random_rays(R, 5)
+    z = nb.ops.stratified_z(torch.linspace(0., 1., S, device=DEV), None, R, 2.0, 6.0)
+    full, _ = nb.ops.mlp_fwd_rays(m, T(o), T(d), z, 1.0, nb._lib.PREC_BF16, False)
+    dens, _ = nb.ops.mlp_fwd_rays(m, T(o), T(d), z, 1.0, nb._lib.PREC_BF16, False, density_only=True)
+    assert torch.equal(dens[..., 3], full[..., 3])
+    assert float(dens[..., :3].abs().max()) == 0.0
+    with pytest.raises(RuntimeError):
+        nb.ops.mlp_fwd_rays(m, T(o), T(d), z, 1.0, nb._lib.PREC_BF16, True, density_only=True)
+    for prec in ("bf16", "fp32"):
+        m2, _ = make_model(nb, 3, prec)
+        r = nb.NeRFRenderer(m2, DEV, perturb=0.0)
+        img = r.render(T(o), T(d), R, 1, 1.0, chunk=300)
+        with torch.no_grad():
+            ref = torch.cat([r._render_rays(T(o)[i:i + 300], T(d)[i:i + 300])["rgb_map"] for i in range(0, R, 300)])
+        assert torch.equal(img.view(R, 3), ref), prec
