@@ -1,9 +1,9 @@
 #!/bin/bash
-# Round-1 (second session) evidence collection: gpurun -- bash profiles/collect_r01b.sh
+# Round-1 evidence collection (final of the round): gpurun -- bash profiles/collect_r01c.sh
 # Every ncu pass runs only after the same command exited 0 without ncu.
 set -u
 cd "$(dirname "$0")/.."
-O=gpurun_out/r01b
+O=gpurun_out/r01c
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.txt 2>&1
 python bench.py --steps 20 --warmup 5 > $O/bench_train.json 2> $O/bench_train.err
@@ -20,10 +20,19 @@ ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -s
     python tests/tc_bench.py 16384 192 2 0 > $O/ncu_fwd.log 2>&1
 # full capture: one training step's MLP kernels at the BASELINE size (1024 rays): coarse fwd, fwd-save, dgrad, wgrad, heads
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/plain_train_nograph.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"mlp_tc_kernel|wgrad_tc|heads_wgrad|composite|sample_pdf|adam|train_prepare|pack_kernel|mse" -s 40 -c 22 -f -o $O/train_step \
+ncu --set full --clock-control none --import-source on -k regex:"mlp_tc_kernel|wgrad_tc|heads_wgrad|composite|sample_pdf|adam|train_prepare|pack_kernel|mse" -s 38 -c 22 -f -o $O/train_step \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/ncu_train_step.log 2>&1
 # HBM-bound ray kernels at the 640k-ray render size (16384-ray chunks)
 python bench.py --workload render --steps 1 --warmup 3 --no-cpu-baseline > $O/plain_render.log 2>&1 &&
 ncu --set full --clock-control none -k regex:"composite_fwd|sample_pdf|stratified" -s 12 -c 6 -f -o $O/ray_kernels \
     python bench.py --workload render --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_ray_kernels.log 2>&1
+ls -la $O
+# the other BASELINE configs (one line each)
+python bench.py --samples 256 --importance 256 --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_train_stress_256_256.json 2>/dev/null
+python bench.py --workload render --rays 262144 --samples 256 --importance 256 --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_render_stress_256_256.json 2>/dev/null
+python bench.py --workload render --rays 10000 --steps 5 --warmup 3 > $O/bench_render_100x100_bf16.json 2>/dev/null
+python bench.py --workload render --rays 10000 --precision fp32 --steps 3 --warmup 3 --no-cpu-baseline > $O/bench_render_100x100_fp32.json 2>/dev/null
+python bench.py --rays 4096 --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_train_4096.json 2>/dev/null
+python bench.py --workload render --impl reference --steps 3 --warmup 1 > $O/bench_reference_render.json 2>/dev/null
+python tests/hbm_bw.py > $O/hbm_bw.txt 2>&1
 ls -la $O
