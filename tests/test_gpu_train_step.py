@@ -101,6 +101,28 @@ def test_eager_and_graph_match_autograd_path(nb, precision, perturb):
         assert np.mean(np.abs(p - ref_p) <= 2e-5) > 0.85, kind
 
 
+def test_renderer_knobs_inside_the_graph(nb):
+    """raw_noise_std > 0 (torch.randn draws captured in the graph, reference order renderer.py:60,136,182,136),
+    black background, coord_scale != 1, non-default near/far and sample counts: graph replay == autograd path."""
+    R, n = 64, 2
+    o, d, tgt = batch(R, 17)
+    res = {}
+    for kind in ("autograd", "graph"):
+        m, _, opt = make(nb, 11, "bf16", 1.0)
+        r = nb.NeRFRenderer(m, DEV, N_samples=32, N_importance=48, near=1.5, far=5.0, white_bkgd=False, perturb=1.0,
+                            raw_noise_std=0.5, coord_scale=0.7)
+        torch.manual_seed(9)
+        if kind == "autograd":
+            losses = autograd_steps(nb, m, r, opt, o, d, tgt, n)
+        else:
+            step = nb.TrainStep(r, opt, R)
+            torch.manual_seed(9)
+            losses = [float(step(o, d, tgt)) for _ in range(n)]
+        res[kind] = losses
+    assert res["graph"][0] == res["autograd"][0]
+    np.testing.assert_allclose(res["graph"], res["autograd"], rtol=2e-4)
+
+
 def test_construction_does_not_train(nb):
     m, r, opt = make(nb, 3, "bf16", 1.0)
     before = m.flat_params.clone()
