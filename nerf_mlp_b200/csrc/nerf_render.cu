@@ -280,30 +280,67 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(PdfArgs a) {
     const float s = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));                              // :197
     if (a.samples != nullptr) a.samples[(int64_t)r * a.N_imp + j] = s;
     if (a.inds != nullptr) a.inds[(int64_t)r * a.N_imp + j] = (int64_t)lo;
-    if (kMerge) sortbuf[a.S_c + j] = s;
+    if (kMerge) sortbuf[j] = s;
   }
   if (kMerge) {
     // z_fine = sort(cat[z_coarse, z_samples])                                                   // :90
+    // A true multiset sort (bit-identical to torch.sort's values): bitonic-sort the N_imp samples, then
+    // merge them with the coarse depths by rank (two binary searches per element) -- 2.5x fewer
+    // compare-exchange steps than sorting all S_c + N_imp values.  The coarse depths are sorted by
+    // construction (renderer.py:52-61); if a caller passes unsorted ones everything is sorted instead.
     const int n = a.S_c + a.N_imp;
-    int npad = 64;
-    while (npad < n) npad <<= 1;
     const float* z = a.z_coarse + (int64_t)r * a.S_c;
-    for (int k = lane; k < a.S_c; k += 32) sortbuf[k] = z[k];
-    for (int k = n + lane; k < npad; k += 32) sortbuf[k] = CUDART_INF_F;
-    __syncwarp();
-    for (int size = 2; size <= npad; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int i = lane; i < (npad >> 1); i += 32) {
-          const int lo_i = 2 * i - (i & (stride - 1));       // index with bit `stride` cleared
-          const int hi_i = lo_i + stride;
-          const bool up = (lo_i & size) == 0;
-          const float x = sortbuf[lo_i], y = sortbuf[hi_i];
-          if ((x > y) == up) { sortbuf[lo_i] = y; sortbuf[hi_i] = x; }
+    float* zc = sortbuf + kMaxBins;                  // coarse depths  [S_c]
+    float* merged = cdf;                             // cdf | bins are dead now: [2 * kMaxBins] >= n
+    bool sorted_in = a.N_imp <= kMaxBins;            // (the sample region of sortbuf must not reach zc)
+    for (int k = lane; k + 1 < a.S_c; k += 32)
+      if (z[k + 1] < z[k]) sorted_in = false;
+    sorted_in = __all_sync(0xffffffffu, sorted_in);
+    auto bitonic = [&](float* buf, int npad) {
+      for (int size = 2; size <= npad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int i = lane; i < (npad >> 1); i += 32) {
+            const int lo_i = 2 * i - (i & (stride - 1));       // index with bit `stride` cleared
+            const int hi_i = lo_i + stride;
+            const bool up = (lo_i & size) == 0;
+            const float x = buf[lo_i], y = buf[hi_i];
+            if ((x > y) == up) { buf[lo_i] = y; buf[hi_i] = x; }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
+    };
+    if (sorted_in) {
+      int npad = 64;
+      while (npad < a.N_imp) npad <<= 1;
+      for (int k = a.N_imp + lane; k < npad; k += 32) sortbuf[k] = CUDART_INF_F;
+      for (int k = lane; k < a.S_c; k += 32) zc[k] = z[k];
+      __syncwarp();
+      bitonic(sortbuf, npad);
+      for (int i = lane; i < a.S_c; i += 32) {       // rank of a coarse depth among the samples: #{j : zs[j] < a}
+        const float v = zc[i];
+        int lo = 0, hi = a.N_imp;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sortbuf[mid] < v) lo = mid + 1; else hi = mid; }
+        merged[i + lo] = v;
+      }
+      for (int j = lane; j < a.N_imp; j += 32) {     // rank of a sample among the coarse depths: #{i : zc[i] <= b}
+        const float v = sortbuf[j];
+        int lo = 0, hi = a.S_c;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (zc[mid] <= v) lo = mid + 1; else hi = mid; }
+        merged[j + lo] = v;
+      }
+    } else {
+      int npad = 64;
+      while (npad < n) npad <<= 1;
+      __syncwarp();
+      for (int k = lane; k < a.N_imp; k += 32) merged[a.S_c + k] = sortbuf[k];
+      for (int k = lane; k < a.S_c; k += 32) merged[k] = z[k];
+      for (int k = n + lane; k < npad; k += 32) merged[k] = CUDART_INF_F;
+      __syncwarp();
+      bitonic(merged, npad);
     }
-    for (int k = lane; k < n; k += 32) a.z_fine[(int64_t)r * n + k] = sortbuf[k];
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) a.z_fine[(int64_t)r * n + k] = merged[k];
   }
 }
 

@@ -186,7 +186,7 @@ def test_sample_pdf_strided_views(nb, st):
 
 
 @pytest.mark.parametrize("S_c,N_imp,det", [(64, 128, True), (64, 128, False), (256, 256, False), (17, 5, True),
-                                           (512, 512, False)])
+                                           (512, 512, False), (300, 700, False), (40, 33, False)])
 def test_resample_merge(nb, S_c, N_imp, det):
     rng = np.random.default_rng(S_c + N_imp)
     R = 21
@@ -206,6 +206,23 @@ def test_resample_merge(nb, S_c, N_imp, det):
     assert np.all(np.diff(z_fine, axis=-1) >= 0)
     # production path (no check exports) gives the same z_fine
     assert np.array_equal(N(nb.ops.resample_merge(T(z), T(w), T(u))), z_fine)
+
+
+def test_resample_merge_unsorted_coarse_depths(nb):
+    """The rank-merge needs sorted coarse depths; unsorted ones (never produced by the reference, renderer.py:52-61)
+    take the full-sort path: z_fine is still the exact multiset sort."""
+    rng = np.random.default_rng(5)
+    R, S_c, N_imp = 9, 64, 128
+    z = rng.uniform(2, 6, (R, S_c)).astype(np.float32)          # unsorted
+    z[0] = np.sort(z[0])
+    w = rng.uniform(0, 1, (R, S_c)).astype(np.float32)
+    u = rng.uniform(0, 1, (R, N_imp)).astype(np.float32)
+    z_fine, zs, _, _ = (N(t) for t in nb.ops.resample_merge(T(z), T(w), T(u), check_mode=True))
+    assert np.array_equal(z_fine, np.sort(np.concatenate([z, zs], -1), -1))
+    # ties between the two runs and repeated values
+    z2 = np.sort(rng.integers(2, 6, (R, S_c)).astype(np.float32), -1)
+    z_fine, zs, _, _ = (N(t) for t in nb.ops.resample_merge(T(z2), T(w), T(u), check_mode=True))
+    assert np.array_equal(z_fine, np.sort(np.concatenate([z2, zs], -1), -1))
 
 
 def test_sort_merge_golden(nb, st):
