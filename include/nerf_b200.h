@@ -166,6 +166,23 @@ int nerf_mse_loss(const float* pred, const float* target, int64_t n, float* loss
 int nerf_train_prepare(double* state, const float* loss, const float* flat_grads, int64_t n, void* stream);
 int nerf_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                        const double* state, void* stream);
+/* nerf_train_prepare + nerf_adam_step_dev as ONE launch (same arithmetic, same state block, same metrics);
+ * `scratch`: nerf_adam_fused_scratch_bytes(n) bytes, zero-initialised once by the caller. */
+size_t nerf_adam_fused_scratch_bytes(int64_t n);
+int nerf_adam_step_fused(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                         double* state, const float* loss, void* scratch, void* stream);
+
+/* The fine-pass compositing of a training step in ONE launch (scripts/train.py:374-382 around
+ * renderer.py:106-107): nerf_composite_fwd -> rgb/depth/acc maps; loss = mean((rgb_map - target)^2) (:376) and
+ * its gradient 2 (rgb_map - target) / (3R); nerf_composite_bwd of that gradient -> d_raw[R,S,4]; and, because
+ * it is the last launch before the weight-gradient kernels, optimizer.zero_grad(): zero_buf[zero_n] (nullable)
+ * is cleared.  `scratch`: nerf_composite_train_scratch_bytes(R) bytes, zero-initialised once by the caller.
+ * Bit-identical to the three separate entry points (loss: same fp64 sum, block-ordered). */
+size_t nerf_composite_train_scratch_bytes(int R);
+int nerf_composite_train(const float* raw, const float* z_vals, const float* rays_d, const float* noise, int R,
+                         int S, int white_bkgd, const float* target, float* rgb_map, float* depth_map,
+                         float* acc_map, float* d_raw, float* loss, void* scratch, float* zero_buf,
+                         int64_t zero_n, void* stream);
 
 /* ---- the callers either side of the path, on the device ----------
  * nerf_generate_rays: rays (and optionally target colours) of n flat ray ids

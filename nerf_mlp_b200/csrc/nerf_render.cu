@@ -94,14 +94,11 @@ __device__ __forceinline__ double warp_scan_add(double p, int lane) {
   return p;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
-                     const float* __restrict__ rays_d, const float* __restrict__ noise, int R, int S,
-                     int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ depth_map,
-                     float* __restrict__ acc_map, float* __restrict__ weights) {
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (r >= R) return;
+// One ray per warp: returns (all lanes) the composited rgb / depth / acc; writes weights if asked.
+struct RayMaps { float r, g, b, depth, acc; };
+__device__ __forceinline__ RayMaps composite_fwd_ray(const float4* __restrict__ raw, const float* __restrict__ z_vals,
+                                                     const float* __restrict__ rays_d, const float* __restrict__ noise,
+                                                     int r, int S, int white_bkgd, float* __restrict__ weights, int lane) {
   const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
   const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
   const int64_t base = (int64_t)r * S;
@@ -134,34 +131,40 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
     z_cur = z_nb;
   }
   ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aa = warp_sum(aa);
+  if (white_bkgd) {                                                                        // :160-161
+    const float bg = 1.f - aa;
+    ar += bg; ag += bg; ab += bg;
+  }
+  return RayMaps{ar, ag, ab, ad, aa};
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
+                     const float* __restrict__ rays_d, const float* __restrict__ noise, int R, int S,
+                     int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ depth_map,
+                     float* __restrict__ acc_map, float* __restrict__ weights) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const RayMaps m = composite_fwd_ray(raw, z_vals, rays_d, noise, r, S, white_bkgd, weights, lane);
   if (lane == 0) {
-    if (white_bkgd) {                                                                      // :160-161
-      const float bg = 1.f - aa;
-      ar += bg; ag += bg; ab += bg;
-    }
-    rgb_map[3 * r] = ar; rgb_map[3 * r + 1] = ag; rgb_map[3 * r + 2] = ab;
-    depth_map[r] = ad;
-    acc_map[r] = aa;
+    rgb_map[3 * r] = m.r; rgb_map[3 * r + 1] = m.g; rgb_map[3 * r + 2] = m.b;
+    depth_map[r] = m.depth;
+    acc_map[r] = m.acc;
   }
 }
 
 // Analytic backward.  Two sweeps over the ray: (1) total = sum_k w_k g_k,
 // (2) prefix sums so that suffix_{>i} = total - prefix_i; both in fp64 (the kernel is HBM-bound).
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
-                     const float* __restrict__ rays_d, const float* __restrict__ noise, int R, int S,
-                     int white_bkgd, const float* __restrict__ d_rgb, const float* __restrict__ d_depth,
-                     const float* __restrict__ d_acc, const float* __restrict__ d_weights,
-                     float4* __restrict__ d_raw) {
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (r >= R) return;
+// gA is the upstream gradient of acc_map BEFORE the white-background term is folded in.
+__device__ __forceinline__ void composite_bwd_ray(const float4* __restrict__ raw, const float* __restrict__ z_vals,
+                                                  const float* __restrict__ rays_d, const float* __restrict__ noise,
+                                                  int r, int S, int white_bkgd, float gR, float gG, float gB, float gD,
+                                                  float gA, const float* __restrict__ d_weights,
+                                                  float4* __restrict__ d_raw, int lane) {
   const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
   const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
   const int64_t base = (int64_t)r * S;
-  const float gR = d_rgb[3 * r], gG = d_rgb[3 * r + 1], gB = d_rgb[3 * r + 2];
-  const float gD = d_depth != nullptr ? d_depth[r] : 0.f;
-  float gA = d_acc != nullptr ? d_acc[r] : 0.f;
   if (white_bkgd) gA -= (gR + gG + gB);   // rgb_map += 1 - acc
   double total = 0.0;
   for (int sweep = 0; sweep < 2; ++sweep) {
@@ -207,6 +210,78 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
       z_cur = z_nb;
     }
     if (sweep == 0) total = warp_sum(total);
+  }
+}
+
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
+                     const float* __restrict__ rays_d, const float* __restrict__ noise, int R, int S,
+                     int white_bkgd, const float* __restrict__ d_rgb, const float* __restrict__ d_depth,
+                     const float* __restrict__ d_acc, const float* __restrict__ d_weights,
+                     float4* __restrict__ d_raw) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  composite_bwd_ray(raw, z_vals, rays_d, noise, r, S, white_bkgd, d_rgb[3 * r], d_rgb[3 * r + 1], d_rgb[3 * r + 2],
+                    d_depth != nullptr ? d_depth[r] : 0.f, d_acc != nullptr ? d_acc[r] : 0.f, d_weights, d_raw, lane);
+}
+
+// Training pass of the FINE samples in one launch (scripts/train.py:374-382 around renderer.py:106-107):
+// composite -> rgb_map; d_rgb = 2 (rgb - target) / (3R) (the gradient of mean((rgb-target)^2), :376);
+// analytic backward -> d_raw; loss as a deterministic two-level fp64 reduction (per-block partials in
+// `scratch`, summed in block order by the last block to finish); and, folded in because this is the
+// last launch before the weight-gradient kernels, optimizer.zero_grad() of the flat gradient buffer.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_train_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals, const float* __restrict__ rays_d,
+                       const float* __restrict__ noise, int R, int S, int white_bkgd, const float* __restrict__ target,
+                       float* __restrict__ rgb_map, float* __restrict__ depth_map, float* __restrict__ acc_map,
+                       float4* __restrict__ d_raw, float* __restrict__ loss, double* __restrict__ scratch,
+                       float4* __restrict__ zero_buf, int64_t zero_n4) {
+  __shared__ double part[kWarpsPerBlock];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_n4; i += (int64_t)gridDim.x * blockDim.x)
+    zero_buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int r = blockIdx.x * kWarpsPerBlock + warp;
+  double sq = 0.0;
+  if (r < R) {
+    const RayMaps m = composite_fwd_ray(raw, z_vals, rays_d, noise, r, S, white_bkgd, nullptr, lane);
+    const float scale = 2.f / (float)(3 * (int64_t)R);
+    const float e0 = m.r - target[3 * r], e1 = m.g - target[3 * r + 1], e2 = m.b - target[3 * r + 2];
+    sq = (double)e0 * (double)e0 + (double)e1 * (double)e1 + (double)e2 * (double)e2;
+    if (lane == 0) {
+      rgb_map[3 * r] = m.r; rgb_map[3 * r + 1] = m.g; rgb_map[3 * r + 2] = m.b;
+      depth_map[r] = m.depth;
+      acc_map[r] = m.acc;
+    }
+    composite_bwd_ray(raw, z_vals, rays_d, noise, r, S, white_bkgd, scale * e0, scale * e1, scale * e2, 0.f, 0.f, nullptr,
+                      d_raw, lane);
+  }
+  if (lane == 0) part[warp] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) s += part[w];
+    scratch[1 + blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned int*>(scratch), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  // last block: the threads add the per-block partials (fixed assignment and tree => deterministic)
+  __threadfence();
+  double tot = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) tot += *(volatile double*)(scratch + 1 + b);
+  tot = warp_sum(tot);
+  __syncthreads();
+  if (lane == 0) part[warp] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tot = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) tot += part[w];
+    *reinterpret_cast<unsigned int*>(scratch) = 0u;
+    *loss = (float)(tot / (double)(3 * (int64_t)R));
   }
 }
 
@@ -430,6 +505,27 @@ extern "C" int nerf_composite_bwd(const float* raw, const float* z_vals, const f
       (const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, d_rgb_map, d_depth, d_acc, d_weights,
       (float4*)d_raw);
   NERF_LAUNCH_CHECK("composite_bwd_kernel");
+  return 0;
+}
+
+extern "C" size_t nerf_composite_train_scratch_bytes(int R) {
+  return (size_t)(1 + ceil_div(R > 0 ? R : 1, kWarpsPerBlock)) * sizeof(double);
+}
+
+extern "C" int nerf_composite_train(const float* raw, const float* z_vals, const float* rays_d, const float* noise, int R,
+                                    int S, int white_bkgd, const float* target, float* rgb_map, float* depth_map,
+                                    float* acc_map, float* d_raw, float* loss, void* scratch, float* zero_buf,
+                                    int64_t zero_n, void* stream) {
+  NERF_CHECK_ARG(R >= 1 && S >= 1, "nerf_composite_train: bad shape R=%d S=%d", R, S);
+  NERF_CHECK_ARG(raw && z_vals && rays_d && target && rgb_map && depth_map && acc_map && d_raw && loss && scratch,
+                 "nerf_composite_train: null pointer");
+  NERF_CHECK_ARG((((uintptr_t)raw | (uintptr_t)d_raw | (uintptr_t)zero_buf) & 15) == 0 && ((uintptr_t)scratch & 7) == 0,
+                 "nerf_composite_train: raw/d_raw/zero_buf must be 16-byte aligned, scratch 8-byte aligned");
+  NERF_CHECK_ARG(zero_n >= 0 && (zero_n & 3) == 0, "nerf_composite_train: zero_n must be a multiple of 4 (got %lld)", (long long)zero_n);
+  composite_train_kernel<<<ceil_div(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      (const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, target, rgb_map, depth_map, acc_map, (float4*)d_raw, loss,
+      (double*)scratch, (float4*)zero_buf, zero_buf != nullptr ? zero_n / 4 : 0);
+  NERF_LAUNCH_CHECK("composite_train_kernel");
   return 0;
 }
 

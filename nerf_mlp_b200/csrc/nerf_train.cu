@@ -76,9 +76,84 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
   v[i] = vi;
 }
 
+// train_prepare_kernel + adam_dev_kernel in one launch: every block derives the step's scalars from the
+// state block itself (thread 0, double arithmetic), updates its 256 parameters and leaves the sum of
+// squares of its gradients in `scratch`; the last block to finish adds the partials in block order,
+// fills the metrics and advances the step counter (no other block reads the state after that).
+__global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, int64_t n, double* __restrict__ st,
+                                                         const float* __restrict__ loss, double* __restrict__ scratch) {
+  __shared__ float sc[7];
+  __shared__ double part[8];
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const double lr = st[0], b1 = st[1], b2 = st[2], step = st[5] + 1.0;
+    const double bc1 = 1.0 - pow(b1, step), bc2 = 1.0 - pow(b2, step);
+    sc[0] = (float)(1.0 - b1); sc[1] = (float)b2; sc[2] = (float)(1.0 - b2);
+    sc[3] = (float)(-(lr / bc1)); sc[4] = (float)sqrt(bc2); sc[5] = (float)st[3]; sc[6] = (float)st[4];
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double sq = 0.0;
+  if (i < n) {
+    const float graw = g[i];
+    sq = (double)graw * (double)graw;
+    const float gi = graw * sc[6];
+    float mi = m[i], vi = v[i];
+    mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(gi, mi), sc[0]));
+    vi = __fadd_rn(__fmul_rn(vi, sc[1]), __fmul_rn(__fmul_rn(gi, gi), sc[2]));
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), sc[4]), sc[5]);
+    p[i] = __fadd_rn(p[i], __fdiv_rn(__fmul_rn(sc[3], mi), denom));
+    m[i] = mi;
+    v[i] = vi;
+  }
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += part[w];
+    scratch[1 + blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned int*>(scratch), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  // last block: all 256 threads add the per-block partials (fixed assignment and tree => deterministic)
+  __threadfence();
+  double ss = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) ss += *(volatile double*)(scratch + 1 + b);
+  ss = warp_sum(ss);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ss = 0.0;
+    for (int w = 0; w < 8; ++w) ss += part[w];
+    *reinterpret_cast<unsigned int*>(scratch) = 0u;
+    const double l = loss != nullptr ? (double)*loss : 0.0;
+    st[5] = st[5] + 1.0;
+    st[10] = l;
+    st[11] = l > 0.0 ? 10.0 * log10(1.0 / l) : INFINITY;
+    st[12] = sqrt(ss) * fabs(st[4]);
+  }
+}
+
 }  // namespace nerf
 
 using namespace nerf;
+
+extern "C" size_t nerf_adam_fused_scratch_bytes(int64_t n) { return (size_t)(1 + ceil_div(n > 0 ? n : 1, 256)) * sizeof(double); }
+
+extern "C" int nerf_adam_step_fused(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                    double* state, const float* loss, void* scratch, void* stream) {
+  NERF_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state && scratch && n >= 1, "nerf_adam_step_fused: bad arguments");
+  NERF_CHECK_ARG((((uintptr_t)state | (uintptr_t)scratch) & 7) == 0, "nerf_adam_step_fused: state/scratch must be 8-byte aligned");
+  adam_fused_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, state, loss,
+                                                                        (double*)scratch);
+  NERF_LAUNCH_CHECK("adam_fused_kernel");
+  return 0;
+}
 
 extern "C" int nerf_train_prepare(double* state, const float* loss, const float* flat_grads, int64_t n, void* stream) {
   NERF_CHECK_ARG(state != nullptr && flat_grads != nullptr && n >= 1, "nerf_train_prepare: bad arguments");

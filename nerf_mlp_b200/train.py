@@ -74,6 +74,9 @@ class TrainStep:
         self.target = torch.zeros((self.R, 3), **f32)
         self.state = torch.zeros(_lib.TRAIN_STATE_DOUBLES, device=self.dev, dtype=torch.float64)
         self._loss = torch.zeros((), **f32)
+        self._scratch_c = torch.zeros(int(dll().nerf_composite_train_scratch_bytes(self.R)) // 8, device=self.dev, dtype=torch.float64)
+        self._scratch_a = torch.zeros(int(dll().nerf_adam_fused_scratch_bytes(m.flat_params.numel())) // 8, device=self.dev,
+                                      dtype=torch.float64)
         self._lr_pushed = None
         self._step_pushed = None
         self.use_graph = bool(graph)
@@ -149,13 +152,16 @@ class TrainStep:
         self._mark("resample_merge")
         raw1, ws = ops.mlp_fwd_rays(m, o, d, z_fine, cs, prec, True)
         self._mark("mlp_fwd_fine_save")
-        rgb, depth, acc, _ = ops.composite_fwd(raw1, z_fine, d, noise1, white, False)
-        d_rgb = torch.empty_like(rgb)
-        check(dll().nerf_mse_loss(ptr(rgb), ptr(self.target), rgb.numel(), ptr(self._loss), ptr(d_rgb),
-                                  stream_ptr(self.dev)), "nerf_mse_loss")
-        d_raw = ops.composite_bwd(raw1, z_fine, d, noise1, white, d_rgb)
-        m._flat_grad.zero_()                                                 # optimizer.zero_grad()
-        self._mark("composite_fwd_fine+mse+composite_bwd")
+        # fine compositing + MSE + its gradient + compositing backward + zero_grad: ONE launch (nerf_composite_train)
+        f32 = dict(device=self.dev, dtype=torch.float32)
+        rgb, depth, acc = torch.empty((R, 3), **f32), torch.empty((R,), **f32), torch.empty((R,), **f32)
+        d_raw = torch.empty((R, z_fine.shape[1], 4), **f32)
+        d_rgb = None
+        check(dll().nerf_composite_train(ptr(raw1), ptr(z_fine), ptr(d), ptr(noise1), R, z_fine.shape[1], int(white),
+                                         ptr(self.target), ptr(rgb), ptr(depth), ptr(acc), ptr(d_raw), ptr(self._loss),
+                                         ptr(self._scratch_c), ptr(m._flat_grad), m._flat_grad.numel(),
+                                         stream_ptr(self.dev)), "nerf_composite_train")
+        self._mark("composite_train(fwd+mse+bwd+zero_grad)")
         if self.stage_events:                                                # same launches, one mark in between
             ops.mlp_bwd(m, d_raw, ws, prec, m._flat_grad, z_fine.shape[1], _lib.BWD_DGRAD)
             self._mark("mlp_bwd_dgrad")
@@ -175,9 +181,9 @@ class TrainStep:
         st = stream_ptr(self.dev)
         if self._world() > 1:
             self._mark("grad_allreduce")
-        check(dll().nerf_train_prepare(ptr(self.state), ptr(self._loss), ptr(m._flat_grad), n, st), "nerf_train_prepare")
-        check(dll().nerf_adam_step_dev(ptr(m.flat_params), ptr(m._flat_grad), ptr(opt._m), ptr(opt._v), n,
-                                       ptr(self.state), st), "nerf_adam_step_dev")
+        # metrics (loss, PSNR, grad norm) + step counter + Adam: ONE launch (nerf_adam_step_fused)
+        check(dll().nerf_adam_step_fused(ptr(m.flat_params), ptr(m._flat_grad), ptr(opt._m), ptr(opt._v), n,
+                                         ptr(self.state), ptr(self._loss), ptr(self._scratch_a), st), "nerf_adam_step_fused")
         if r_is_bf16(self.renderer):
             check(dll().nerf_pack_weights(ptr(m.flat_params), ptr(m._packed), st), "nerf_pack_weights")
         self._mark("metrics+adam+repack")

@@ -255,3 +255,56 @@ def test_mse_loss(nb):
     loss.backward()
     assert abs(float(loss) - float(np.mean((a.astype(np.float64) - b) ** 2))) < 1e-7
     np.testing.assert_allclose(N(pa.grad), 2 * (a - b) / a.size, atol=1e-9, rtol=1e-6)
+
+
+def test_fused_training_entry_points(nb):
+    """nerf_composite_train == nerf_composite_fwd + nerf_mse_loss + nerf_composite_bwd (+ zero_grad), and
+    nerf_adam_step_fused == nerf_train_prepare + nerf_adam_step_dev: bit-identical outputs (the loss /
+    gradient norm are fp64 sums in a different, still fixed, order: equal to 1e-7 relative)."""
+    from nerf_mlp_b200._lib import dll, ptr, stream_ptr, check
+    rng = np.random.default_rng(9)
+    for R, S, wb, with_noise in ((100, 192, True, False), (37, 65, False, True)):
+        raw = T((rng.standard_normal((R, S, 4)) * np.array([2, 2, 2, 4])).astype(np.float32))
+        z = T(np.sort(rng.uniform(2, 6, (R, S)).astype(np.float32), -1))
+        d = T(rng.standard_normal((R, 3)).astype(np.float32))
+        tgt = T(rng.uniform(0, 1, (R, 3)).astype(np.float32))
+        noise = T(rng.standard_normal((R, S)).astype(np.float32)) if with_noise else None
+        rgb, depth, acc, _ = nb.ops.composite_fwd(raw, z, d, noise, wb, False)
+        loss = nb.ops.mse_loss(rgb.clone().requires_grad_(True), tgt)
+        d_rgb = (2.0 / rgb.numel()) * (rgb - tgt)
+        d_raw = nb.ops.composite_bwd(raw, z, d, noise, wb, d_rgb.contiguous())
+        f32 = dict(device=DEV, dtype=torch.float32)
+        rgb2, dep2, acc2 = torch.empty(R, 3, **f32), torch.empty(R, **f32), torch.empty(R, **f32)
+        d_raw2, loss2 = torch.empty(R, S, 4, **f32), torch.zeros((), **f32)
+        zero_me = torch.ones(1000, **f32)
+        scratch = torch.zeros(int(dll().nerf_composite_train_scratch_bytes(R)) // 8, device=DEV, dtype=torch.float64)
+        for _ in range(2):                                 # twice: the scratch counter resets itself
+            check(dll().nerf_composite_train(ptr(raw), ptr(z), ptr(d), ptr(noise), R, S, int(wb), ptr(tgt), ptr(rgb2), ptr(dep2),
+                                             ptr(acc2), ptr(d_raw2), ptr(loss2), ptr(scratch), ptr(zero_me), 1000,
+                                             stream_ptr(torch.device(DEV))), "nerf_composite_train")
+        assert torch.equal(rgb2, rgb) and torch.equal(dep2, depth) and torch.equal(acc2, acc)
+        assert torch.equal(d_raw2, d_raw)
+        assert abs(float(loss2) - float(loss)) <= 1e-7 * float(loss)
+        assert float(zero_me.abs().max()) == 0.0
+    # fused Adam
+    n = 595844
+    g = T(rng.standard_normal(n).astype(np.float32) * 1e-3)
+    outs = []
+    for fused in (False, True):
+        p = T(np.linspace(-1, 1, n, dtype=np.float32)); m = torch.zeros_like(p); v = torch.zeros_like(p)
+        st = torch.zeros(nb._lib.TRAIN_STATE_DOUBLES, device=DEV, dtype=torch.float64)
+        st[:6] = torch.tensor([5e-4, 0.9, 0.999, 1e-8, 0.5, 3.0], dtype=torch.float64)
+        lossv = T(np.array(0.0123, np.float32))
+        scratch = torch.zeros(int(dll().nerf_adam_fused_scratch_bytes(n)) // 8, device=DEV, dtype=torch.float64)
+        sp = stream_ptr(torch.device(DEV))
+        for _ in range(2):
+            if fused:
+                check(dll().nerf_adam_step_fused(ptr(p), ptr(g), ptr(m), ptr(v), n, ptr(st), ptr(lossv), ptr(scratch), sp), "fused")
+            else:
+                check(dll().nerf_train_prepare(ptr(st), ptr(lossv), ptr(g), n, sp), "prepare")
+                check(dll().nerf_adam_step_dev(ptr(p), ptr(g), ptr(m), ptr(v), n, ptr(st), sp), "adam")
+        outs.append((p.clone(), m.clone(), v.clone(), st.clone()))
+    (p0, m0, v0, s0), (p1, m1, v1, s1) = outs
+    assert torch.equal(p0, p1) and torch.equal(m0, m1) and torch.equal(v0, v1)
+    assert float(s0[5]) == float(s1[5]) == 5.0 and float(s0[10]) == float(s1[10]) and float(s0[11]) == float(s1[11])
+    assert abs(float(s0[12]) - float(s1[12])) <= 1e-12 * float(s0[12])
