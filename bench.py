@@ -51,8 +51,8 @@ N_SAMPLES, N_IMPORTANCE = 64, 128
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 200 train / 5 render)")
+    ap.add_argument("--warmup", type=int, default=None, help="untimed warm-up steps (default: 10 train / 3 render)")
     ap.add_argument("--workload", choices=["train", "render"], default="train")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (train) / total rays (render)")
@@ -62,7 +62,12 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="train: enqueue the step eagerly instead of replaying the CUDA graph")
     ap.add_argument("--autograd", action="store_true", help="train: the reference's loop on the drop-in classes (autograd + FlatAdam)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 200 if args.workload == "train" else 5
+    if args.warmup is None:
+        args.warmup = 10 if args.workload == "train" else 3
+    return args
 
 
 def peaks():
@@ -350,7 +355,6 @@ def main():
     launches = dll.nerf_launch_count() - launches0
     if stage_acc is not None and train_step.use_graph:
         launches = K * train_step.launches_per_step                 # replayed launches are not seen by the host-side counter
-    clocks = sampler.stop()
     ms_steps = [a.elapsed_time(b) for a, b in evs]
     ms_total = torch.tensor([sum(ms_steps)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -370,6 +374,7 @@ def main():
     if world > 1:
         td.all_reduce(e2e_s, op=td.ReduceOp.MAX)
     e2e_val = units_per_step * K / float(e2e_s)
+    clocks = sampler.stop()                                         # sampled over the timed region and the e2e loop
 
     # --- per-stage device times: K more replays of the same step re-captured with an event record between the
     # kernels (the records cost ~4 us each, so they stay out of the timed region above)
