@@ -26,6 +26,12 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# The CPU legs use every host thread: torchrun exports OMP_NUM_THREADS=1 to its workers, which would pin the
+# numpy/OpenBLAS reference arm to one core (set before numpy is first imported).
+if "reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        if os.environ.get(_v, "") in ("", "1"):
+            os.environ[_v] = str(os.cpu_count())
 # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner with printf)
 # get stderr as their fd 1 for the whole run; emit() writes the result line to the real stdout.
 _REAL_STDOUT = os.dup(1)
