@@ -93,11 +93,10 @@ __global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ p, 
     sc[3] = (float)(-(lr / bc1)); sc[4] = (float)sqrt(bc2); sc[5] = (float)st[3]; sc[6] = (float)st[4];
   }
   __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double sq = 0.0;
-  if (i < n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float graw = g[i];
-    sq = (double)graw * (double)graw;
+    sq += (double)graw * (double)graw;
     const float gi = graw * sc[6];
     float mi = m[i], vi = v[i];
     mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(gi, mi), sc[0]));
@@ -149,8 +148,10 @@ extern "C" int nerf_adam_step_fused(float* params, const float* grads, float* ex
                                     double* state, const float* loss, void* scratch, void* stream) {
   NERF_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state && scratch && n >= 1, "nerf_adam_step_fused: bad arguments");
   NERF_CHECK_ARG((((uintptr_t)state | (uintptr_t)scratch) & 7) == 0, "nerf_adam_step_fused: state/scratch must be 8-byte aligned");
-  adam_fused_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, state, loss,
-                                                                        (double*)scratch);
+  // one wave of blocks: every block pays the two double-precision pow() of the bias corrections once
+  const int blocks = ceil_div(n, 256) < 592 ? ceil_div(n, 256) : 592;
+  adam_fused_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, state, loss,
+                                                              (double*)scratch);
   NERF_LAUNCH_CHECK("adam_fused_kernel");
   return 0;
 }
