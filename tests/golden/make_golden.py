@@ -297,9 +297,24 @@ def data_case(name="data_3x12x12"):
     print(name, len(ds), g["all_rays_d"].dtype, g["all_rgbs"].dtype)
 
 
+def render100_case(name="render_pinhole_100x100", seed=8):
+    """BASELINE.json configs[0]: the reference's own `renderer.render` of a 100x100 view (10 000 rays, 64+128
+    samples, fp32, CPU), through the public entry point with its default chunking.  Only the image is kept
+    (float16-free: fp32, 120 KB)."""
+    model, _ = ref_model(seed)
+    r = NeRFRenderer(model, DEV, N_samples=64, N_importance=128, near=2.0, far=6.0, white_bkgd=True, perturb=0.0)
+    o, d, focal = O.pinhole_rays(100, 100)
+    img = r.render(torch.from_numpy(o), torch.from_numpy(d), 100, 100, focal)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), seed=np.array(seed), image=img.numpy())
+    print(name, img.shape, float(img.mean()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "data":
         data_case()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "render100":
+        render100_case()
         sys.exit(0)
     stage_case()
     render_case("render_det_r96", 96, 1)                                   # config-1 shape, small R
@@ -312,3 +327,4 @@ if __name__ == "__main__":
     grad_case()
     adam_case()
     data_case()
+    render100_case()

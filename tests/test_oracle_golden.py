@@ -186,3 +186,16 @@ def test_adam_kat():
     for s in range(3):
         p, m, v = O.adam_step(p, g[f"g{s}"], m, v, s + 1)
         np.testing.assert_allclose(p, g[f"p{s + 1}"], atol=1e-7, rtol=1e-6)
+
+
+def test_render_100x100_rows_against_reference_image():
+    """BASELINE.json configs[0] (100x100 view, 64+128, fp32): the oracle on three image rows (300 rays) against
+    the image the reference's own `renderer.render` produced; same rule as test_render_rays_end_to_end."""
+    g = load_golden("render_pinhole_100x100")
+    p = O.init_params(int(g["seed"]))
+    o, d, _ = O.pinhole_rays(100, 100)
+    rows = np.r_[0:100, 5000:5100, 9900:10000]
+    cfg = O.RenderConfig()
+    out = O.render_rays(p, o[rows], d[rows], cfg, np.linspace(0, 1, 64, dtype=np.float32), np.linspace(0, 1, 128, dtype=np.float32))
+    err = np.abs(out["rgb_map"] - g["image"].reshape(-1, 3)[rows]).max(-1)
+    assert (err <= 1e-4).mean() >= 0.70 and err.max() <= 5e-3, (err.max(), (err <= 1e-4).mean())
