@@ -68,10 +68,10 @@ class TrainStep:
             optimizer._m = torch.zeros_like(m.flat_params)
             optimizer._v = torch.zeros_like(m.flat_params)
         f32 = dict(device=self.dev, dtype=torch.float32)
-        self.rays_o = torch.zeros((self.R, 3), **f32)
-        self.rays_d = torch.zeros((self.R, 3), **f32)
+        self._inputs = torch.zeros((3, self.R, 3), **f32)     # static batch buffers of the captured step (one block)
+        self.rays_o, self.rays_d, self.target = self._inputs[0], self._inputs[1], self._inputs[2]
         self.rays_d[:, 2] = -1.0
-        self.target = torch.zeros((self.R, 3), **f32)
+        self._pipe = None                                     # copy stream / staging of submit()
         self.state = torch.zeros(_lib.TRAIN_STATE_DOUBLES, device=self.dev, dtype=torch.float64)
         self._loss = torch.zeros((), **f32)
         self._scratch_c = torch.zeros(int(dll().nerf_composite_train_scratch_bytes(self.R)) // 8, device=self.dev, dtype=torch.float64)
@@ -279,6 +279,61 @@ class TrainStep:
         self._step_pushed = self.opt._step
         self.opt._opt_called = True
         return self._loss
+
+    # ---- pipelined interface: H2D of the next batch and the metric read-back overlap the running step ----
+    def _pipeline(self):
+        if self._pipe is None:
+            n_slots = 4
+            self._pipe = {
+                "copy_stream": torch.cuda.Stream(self.dev),
+                "stage": torch.zeros_like(self._inputs),
+                "ev_h2d": torch.cuda.Event(), "ev_stage_free": torch.cuda.Event(),
+                "host": [torch.zeros(3, dtype=torch.float64).pin_memory() for _ in range(n_slots)],
+                "done": [torch.cuda.Event() for _ in range(n_slots)],
+                "slot": 0,
+            }
+        return self._pipe
+
+    def submit(self, rays_o, rays_d, target):
+        """Enqueue one step on a batch held in (pinned) HOST memory without waiting for anything:
+        the three H2D copies run on a copy stream while the previous step is still computing (they land in a
+        staging block; one 36 KB device copy moves it into the step's static buffers), the step is replayed,
+        and [loss, psnr, grad_norm] are copied to a pinned slot.  Returns a ticket for :meth:`result`.  Every
+        step still moves its own inputs host->device and its own metrics device->host -- only the waiting is
+        taken off the critical path (the reference blocks on .item() / .cpu() several times per step)."""
+        if rays_o.is_cuda or rays_d.is_cuda or target.is_cuda:
+            self(rays_o, rays_d, target)                      # device-resident batch: nothing to overlap
+            pipe = self._pipeline()
+        else:
+            pipe = self._pipeline()
+            cs, stage = pipe["copy_stream"], pipe["stage"]
+            for src in (rays_o, rays_d, target):
+                if tuple(src.shape) != (self.R, 3):
+                    raise RuntimeError(f"TrainStep: batch shape {tuple(src.shape)} != captured shape {(self.R, 3)}")
+            main = torch.cuda.current_stream(self.dev)
+            cs.wait_event(pipe["ev_stage_free"])              # the previous step has taken its batch out of the stage
+            with torch.cuda.stream(cs):
+                stage[0].copy_(rays_o, non_blocking=True)
+                stage[1].copy_(rays_d, non_blocking=True)
+                stage[2].copy_(target, non_blocking=True)
+                pipe["ev_h2d"].record(cs)
+            main.wait_event(pipe["ev_h2d"])
+            self._inputs.copy_(stage, non_blocking=True)
+            pipe["ev_stage_free"].record(main)
+            self()
+        slot = pipe["slot"]
+        pipe["slot"] = (slot + 1) % len(pipe["host"])
+        pipe["host"][slot].copy_(self.state[_ST_LOSS:_ST_GNORM + 1], non_blocking=True)
+        pipe["done"][slot].record(torch.cuda.current_stream(self.dev))
+        return slot
+
+    def result(self, ticket):
+        """Metrics of the step submitted under `ticket` (blocks until that step has finished; at most
+        len(slots)-1 newer steps may have been submitted since)."""
+        pipe = self._pipeline()
+        pipe["done"][ticket].synchronize()
+        loss, psnr, gnorm = pipe["host"][ticket].tolist()
+        return {"loss": loss, "psnr": psnr, "grad_norm": gnorm}
 
     @property
     def loss(self):
