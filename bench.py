@@ -12,7 +12,7 @@ configs[2], the 800x800 (640k-ray) render sharded over the ranks (strong scaling
 One JSON line on stdout (rank 0).  `value` = whole-job rays/s with inputs resident in HBM;
 `e2e` = the same step through the public API with rays/targets copied from pinned host memory and
 the loss read back every step; `roofline` = the fused MLP forward kernel (fine pass) against the
-measured bf16 tensor peak; `cpu_baseline` = the numpy oracle port timed on this box's host cores.
+measured bf16 tensor peak; `cpu_baseline` = the torch-CPU restatement of the reference timed on this box's host cores.
 `--impl reference` times that CPU path alone (the reference's own algorithm on the host cores).
 """
 import argparse
@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--samples", type=int, default=64, help="coarse samples per ray (BASELINE configs[4] stress: 256)")
     ap.add_argument("--importance", type=int, default=128, help="importance samples per ray (stress: 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-port", choices=["torch", "numpy"], default="torch",
+                    help="CPU legs: torch-CPU restatement of the reference (default) or the numpy checker")
     ap.add_argument("--no-graph", action="store_true", help="train: enqueue the step eagerly instead of replaying the CUDA graph")
     ap.add_argument("--autograd", action="store_true", help="train: the reference's loop on the drop-in classes (autograd + FlatAdam)")
     args = ap.parse_args()
@@ -135,14 +137,35 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port on the host cores (bounded sample)
+# CPU baseline: the reference's algorithm on the host cores (bounded sample)
 # ------------------------------------------------------------------------------------------------
-def cpu_step_fn(workload, rays):
+# Timed port = oracle/nerf_oracle_torch.py: the same torch CPU kernels, in the same order, as the reference's
+# nerfmlp/model.py + renderer.py + the loop body of scripts/train.py (autograd backward, torch.optim.Adam);
+# bit-identical to the reference on the golden vectors (tests/test_oracle_golden.py::test_torch_port_*).
+# `--cpu-port numpy` times the numpy/OpenBLAS checker (oracle/nerf_oracle.py) instead (~2-3x slower).
+CPU_RAYS = {"train": 1024, "render": 2048}
+
+
+def cpu_step_fn(workload, rays, port="torch"):
     import numpy as np
     from oracle import nerf_oracle as O
     p = O.init_params(0)
     o, d = O.random_rays(rays, 1)
     tgt = np.random.default_rng(2).uniform(0, 1, (rays, 3)).astype(np.float32)
+    if port == "torch":
+        import torch
+        from oracle import nerf_oracle_torch as T
+        torch.set_num_threads(os.cpu_count())
+        to, td_, tt = torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(tgt)
+        if workload == "train":
+            tr = T.Trainer(p, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=1.0)
+            return lambda: tr.step(to, td_, tt)
+        pt = T.params_from_numpy(p)
+
+        def render_t():
+            with torch.no_grad():
+                T.render_rays(pt, to, td_, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=0.0)
+        return render_t
     cfg = O.RenderConfig(N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
     t_vals = np.linspace(0, 1, N_SAMPLES, dtype=np.float32)
     u = np.linspace(0, 1, N_IMPORTANCE, dtype=np.float32)
@@ -166,8 +189,15 @@ def cpu_step_fn(workload, rays):
     return train if workload == "train" else render
 
 
-def time_cpu(workload, rays, steps, warmup):
-    fn = cpu_step_fn(workload, rays)
+def cpu_sample_text(workload, rays, port, reps):
+    impl = ("torch CPU restatement of the reference (same torch ops: F.linear / autograd / torch.optim.Adam), fp32"
+            if port == "torch" else "numpy/OpenBLAS fp32 oracle port")
+    what = "train step (render+MSE+backward+Adam)" if workload == "train" else "render"
+    return f"{rays}-ray {what}, {N_SAMPLES}+{N_IMPORTANCE} samples, {impl}, median of {reps}"
+
+
+def time_cpu(workload, rays, steps, warmup, port="torch"):
+    fn = cpu_step_fn(workload, rays, port)
     for _ in range(warmup):
         fn()
     ts = []
@@ -179,15 +209,15 @@ def time_cpu(workload, rays, steps, warmup):
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's algorithm on the host cores (numpy oracle port; the
-    reference itself is pure Python/PyTorch and does not exist on the GPU box), same metric/config,
-    each step a bounded sample of the workload."""
+    """`--impl reference`: the reference's algorithm on the host cores (the torch-CPU restatement; the
+    reference checkout itself does not exist on the GPU box), same metric/config, each step a bounded
+    sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rays = 256 if args.workload == "train" else 512
+    rays = args.rays or (CPU_RAYS[args.workload] if args.cpu_port == "torch" else (256 if args.workload == "train" else 512))
     steps, warmup = min(args.steps, 5), min(args.warmup, 1)
-    sec = time_cpu(args.workload, rays, steps, warmup)
+    sec = time_cpu(args.workload, rays, steps, warmup, args.cpu_port)
     val = rays / sec
     cores = os.cpu_count()
     line = {"impl": "reference", "metric": f"{args.workload}_rays_per_s", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
@@ -195,7 +225,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, rays_override=rays),
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
-                             "sample": f"{rays}-ray {args.workload} step, 64+128 samples, numpy/OpenBLAS fp32, median of {steps}"},
+                             "sample": cpu_sample_text(args.workload, rays, args.cpu_port, steps)},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -209,7 +239,8 @@ def workload_config(args, rays_override=None):
                 "parallelism": f"dp{args.gpus}",
                 "l2": "per-step working set (~1 GB of saved activations) exceeds the 126 MB L2; a 256 MB buffer is also rewritten between timed steps (untimed)"}
     rays = rays_override or args.rays or 640000
-    return {"workload": f"render {rays} rays (800x800), {N_SAMPLES}+{N_IMPORTANCE} samples, chunk 16384, rays sharded over ranks "
+    what = f"render {rays} rays (800x800)" if rays == 640000 else f"render, bounded sample of {rays} of the 640000 rays of an 800x800 view"
+    return {"workload": f"{what}, {N_SAMPLES}+{N_IMPORTANCE} samples, chunk 16384, rays sharded over ranks "
                         "(BASELINE.json configs[2])",
             "rays_total": rays, "N_samples": N_SAMPLES, "N_importance": N_IMPORTANCE, "perturb": 0.0,
             "parallelism": f"rays/{args.gpus}",
@@ -505,10 +536,10 @@ def main():
     elif args.workload == "train":
         line["config"]["step_api"] = "NeRFRenderer._render_rays + loss.backward() + FlatAdam.step (autograd)"
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        rays_cpu = 256 if args.workload == "train" else 512
-        sec = time_cpu(args.workload, rays_cpu, 3, 1)
+        rays_cpu = CPU_RAYS[args.workload] if args.cpu_port == "torch" else (256 if args.workload == "train" else 512)
+        sec = time_cpu(args.workload, rays_cpu, 3, 1, args.cpu_port)
         line["cpu_baseline"] = {"value": rays_cpu / sec, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{rays_cpu}-ray {args.workload} step, 64+128 samples, numpy/OpenBLAS fp32 oracle port, median of 3"}
+                                "sample": cpu_sample_text(args.workload, rays_cpu, args.cpu_port, 3)}
     if rank == 0:
         emit(line)
     if world > 1:
