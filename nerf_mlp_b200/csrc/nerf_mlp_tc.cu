@@ -41,6 +41,11 @@ using namespace ptx;
 // Measured and dropped: dedicated store warps and TMA bulk stores for the tile-image saves (both
 // slower than the per-warp coalesced copies: bulk S2G 0.34 vs 0.31 ms on the 196 608-row save pass).
 constexpr int kThreads = 352;                     // producer, 2 mma issuers, 8 prologue/epilogue warps
+#ifndef NERF_TC_ARRIVE_LANES
+#define NERF_TC_ARRIVE_LANES 1                    // 1 = every thread arrives on "activations ready" (default); 32 = one arrive per warp (measured: no gain, 78.7 vs 79.4 % of peak)
+#endif
+constexpr int kArriveLanes = NERF_TC_ARRIVE_LANES;
+static_assert(kArriveLanes == 1 || kArriveLanes == 32, "arrive per thread or per warp");
 constexpr int kFirstComputeWarp = 3;
 constexpr int kNumGemmsFwd = 10, kNumGemmsBwd = 9;
 
@@ -385,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kRingK; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 2); mbar_init(bar_pfull(s), 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), (kShared ? 256 : 128) * kCtas); mbar_init(bar_acc(t), 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), (kShared ? 256 : 128) / kArriveLanes * kCtas); mbar_init(bar_acc(t), 1); }
     mbar_init(bar_skew, 1);
     fence_mbar_init();
   }
@@ -554,7 +559,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
       }
       __syncwarp();     // lanes read each other's rows: nobody may overwrite them before all are done
     };
-    auto act_arrive = [&](int t) {   // "activations of tile t ready": local, or (peer CTA of a pair) remote at the leader
+    // "activations of tile t ready": local, or (peer CTA of a pair) remote at the leader.  kArriveLanes == 32 is
+    // the fence / __syncwarp / elected-arrive form (one arrive per warp instead of 32); it was measured to make
+    // no difference, so the per-thread arrives are not what stretches the chain epilogue(l) -> MMA(l+1).
+    auto act_arrive = [&](int t) {
+      if (kArriveLanes == 32) { __syncwarp(); if (lane != 0) return; }
       if (kCtas == 2 && rank != 0) mbar_arrive_cluster(mapa(bar_act(t), 0)); else mbar_arrive(bar_act(t));
     };
     uint32_t acc_ph = 0u;                             // bit t = phase of bar_acc(t)

@@ -107,9 +107,11 @@ def _eval_samples(p, rays_o, rays_d, z, coord_scale):
 
 def render_rays(p, rays_o, rays_d, N_samples=64, N_importance=128, near=2.0, far=6.0, white_bkgd=True,
                 perturb=0.0, raw_noise_std=0.0, coord_scale=1.0, t_rand=None, u=None,
-                noise_coarse=None, noise_fine=None):
+                noise_coarse=None, noise_fine=None, z_fine_override=None):
     """Coarse + fine pass of one ray batch (renderer.py:47-112).  Random draws may be supplied
-    (t_rand [R,S_c], u [R,N_imp], noise_*), otherwise they are drawn in the reference's order."""
+    (t_rand [R,S_c], u [R,N_imp], noise_*), otherwise they are drawn in the reference's order.
+    `z_fine_override` (tests): continue the fine pass from given depths -- isolates the stages after the
+    ill-conditioned inverse cdf, as the numpy oracle's option of the same name does."""
     R = rays_o.shape[0]
     dev = rays_o.device
     t = torch.linspace(0.0, 1.0, steps=N_samples, device=dev)
@@ -132,13 +134,15 @@ def render_rays(p, rays_o, rays_d, N_samples=64, N_importance=128, near=2.0, far
         u = torch.linspace(0.0, 1.0, N_importance, device=dev) if perturb == 0.0 else torch.rand([R, N_importance], device=dev)
     z_samples = sample_pdf(z_mid, w[..., 1:-1], u).detach()
     z_fine, _ = torch.sort(torch.cat([z, z_samples], -1), -1)
+    if z_fine_override is not None:
+        z_fine = z_fine_override
     raw_f = _eval_samples(p, rays_o, rays_d, z_fine, coord_scale)
     if raw_noise_std > 0 and noise_fine is None:
         noise_fine = torch.randn_like(raw_f[..., 3]) * raw_noise_std
-    rgb, depth, acc, _ = raw2outputs(raw_f, z_fine, rays_d, white_bkgd, noise_fine)
+    rgb, depth, acc, w_f = raw2outputs(raw_f, z_fine, rays_d, white_bkgd, noise_fine)
     return {"rgb_map": rgb, "depth_map": depth, "acc_map": acc,
             "rgb_map_coarse": rgb0, "depth_map_coarse": depth0, "acc_map_coarse": acc0,
-            "z_fine": z_fine}
+            "z_fine": z_fine, "raw_fine": raw_f.detach(), "weights_fine": w_f.detach(), "weights_coarse": w.detach()}
 
 
 class Trainer:
