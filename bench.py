@@ -189,6 +189,45 @@ def cpu_step_fn(workload, rays, port="torch"):
     return train if workload == "train" else render
 
 
+def time_torch_eager_gpu(workload, dev):
+    """The same restatement (= the reference's arithmetic, bit-identical on the golden vectors) run as eager fp32
+    PyTorch on this GPU: what the reference itself would do if its device were set to cuda.  An extra BASELINE
+    (reported as `torch_eager_gpu`), measured after the timed regions; not the product path, never part of `value`."""
+    import numpy as np
+    import torch
+    from oracle import nerf_oracle as O
+    from oracle import nerf_oracle_torch as T
+    p = O.init_params(0)
+    rays = 1024 if workload == "train" else 16384
+    o, d = O.random_rays(rays, 1)
+    to, td_ = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
+    if workload == "train":
+        tgt = torch.from_numpy(np.random.default_rng(2).uniform(0, 1, (rays, 3)).astype(np.float32)).to(dev)
+        tr = T.Trainer(p, device=dev, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=1.0)
+        fn = lambda: tr.step(to, td_, tgt)
+    else:
+        pt = T.params_from_numpy(p, device=dev)
+
+        def fn():
+            with torch.no_grad():
+                T.render_rays(pt, to, td_, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=0.0)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(dev)
+    reps = 10 if workload == "train" else 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    what = ("1024-ray train step (autograd + torch.optim.Adam)" if workload == "train" else "16384-ray render chunk")
+    return {"value": rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms,
+            "what": f"{what}, {N_SAMPLES}+{N_IMPORTANCE} samples, eager fp32 PyTorch (TF32 off) on the same B200: the reference's own "
+                    "arithmetic (oracle/nerf_oracle_torch.py) with device=cuda; an extra baseline, not the product path"}
+
+
 def cpu_sample_text(workload, rays, port, reps):
     impl = ("torch CPU restatement of the reference (same torch ops: F.linear / autograd / torch.optim.Adam), fp32"
             if port == "torch" else "numpy/OpenBLAS fp32 oracle port")
@@ -540,6 +579,11 @@ def main():
         sec = time_cpu(args.workload, rays_cpu, 3, 1, args.cpu_port)
         line["cpu_baseline"] = {"value": rays_cpu / sec, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": cpu_sample_text(args.workload, rays_cpu, args.cpu_port, 3)}
+    if rank == 0 and not args.no_cpu_baseline and world == 1 and (N_SAMPLES, N_IMPORTANCE) == (64, 128):
+        try:
+            line["torch_eager_gpu"] = time_torch_eager_gpu(args.workload, dev)
+        except Exception as exc:  # a baseline must never take the bench line down
+            line["torch_eager_gpu"] = {"unavailable": repr(exc)[:200]}
     if rank == 0:
         emit(line)
     if world > 1:

@@ -45,6 +45,29 @@ constexpr int kThreads = 352;                     // producer, 2 mma issuers, 8 
 #define NERF_TC_ARRIVE_LANES 1                    // 1 = every thread arrives on "activations ready" (default); 32 = one arrive per warp (measured: no gain, 78.7 vs 79.4 % of peak)
 #endif
 constexpr int kArriveLanes = NERF_TC_ARRIVE_LANES;
+// Separate weight streams per tile ("split" mode).  With ONE shared stream both tiles must consume every slot
+// within ring distance of each other, which locks their MMA phases together: in the save / dgrad kernels (each
+// tile's epilogue on its own four warps) the SM then alternates between "both tiles issue MMAs" and "both
+// tiles run their epilogue" and the tensor pipe idles through every epilogue (cycle counters: 6.2k clk of MMAs,
+// then 5k clk of commit + epilogue + arrive per layer).  With a private half-ring per tile the two chains are
+// decoupled and tile B is started half a period behind tile A, so one tile's MMAs run under the other tile's
+// epilogue.  Costs 2x the L2->SMEM weight bytes (16 B/clk/SM) and half the ring depth per stream.
+#ifndef NERF_TC_SPLIT_TRAIN
+#define NERF_TC_SPLIT_TRAIN 0                     // save-mode forward + dgrad kernels (measured slower: 0.322 / 0.255 vs 0.311 / 0.243 ms)
+#endif
+// Forward kernels: the x-tile (positional encoding) of the NEXT work unit is computed while the compute warps wait
+// for the layer-6 accumulators of the current one (the x-tile's last reader is layer 5), so the unit boundary costs
+// one ordinary layer transition instead of  drain + last epilogue + prologue  (timeline: 6.6k clk of idle tensor
+// pipe per unit of 62k in the inference kernel, 13k of ~100k in the save-mode kernel).
+#ifndef NERF_TC_PIPE_PROLOGUE
+#define NERF_TC_PIPE_PROLOGUE 1
+#endif
+#ifndef NERF_TC_SHARED_TRAIN
+#define NERF_TC_SHARED_TRAIN 0                    // 1: the save / dgrad kernels share every epilogue among all eight warps too
+#endif
+#ifndef NERF_TC_SPLIT_INFER
+#define NERF_TC_SPLIT_INFER 0                     // inference forward (shared epilogues)
+#endif
 static_assert(kArriveLanes == 1 || kArriveLanes == 32, "arrive per thread or per warp");
 constexpr int kFirstComputeWarp = 3;
 constexpr int kNumGemmsFwd = 10, kNumGemmsBwd = 9;
@@ -78,6 +101,14 @@ __device__ unsigned long long g_dbg_clk[8];
 #else
 #define DBG_T(var)
 #define DBG_ACC(i, v)
+#endif
+#ifdef NERF_DBG_TRACE
+// timeline of ONE work unit of CTA 0 (development): writer 0/1 = MMA issuer of tile A/B, 2/3 = warp 3 / warp 7 lane 0
+__device__ long long g_trace[4][160];
+__device__ int g_trace_n[4];
+#define TRACE(w, ok, tag) do { if ((ok) && blockIdx.x == 0 && g_trace_n[w] < 160) g_trace[w][g_trace_n[w]++] = (clock64() << 4) | (tag); } while (0)
+#else
+#define TRACE(w, ok, tag)
 #endif
 __constant__ Slot c_slots[kMaxSlots];          // forward schedule, then the dgrad schedule
 __constant__ PackSlot c_pack[kMaxSlots];
@@ -366,8 +397,11 @@ template <bool kBwd, bool kSave, int kCtas, bool kSigmaOnly = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   static_assert(!kSigmaOnly || (!kBwd && !kSave), "density-only mode is an inference-forward mode");
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr bool kShared = !kBwd && !kSave;             // all eight compute warps share every epilogue
+  constexpr bool kShared = (!kBwd && !kSave) || (NERF_TC_SHARED_TRAIN != 0);   // all eight compute warps share every epilogue
+  constexpr bool kSplit = (!kBwd && !kSave) ? (NERF_TC_SPLIT_INFER != 0) : (NERF_TC_SPLIT_TRAIN != 0);   // private weight stream per tile
   constexpr int kRingK = kRing * kCtas;                 // ring slots per CTA (same bytes, half-size slots in pair mode)
+  constexpr int kRingT = kSplit ? kRingK / 2 : kRingK;  // slots of one stream
+  static_assert(!kSplit || (kRingK % 2 == 0 && kRingT >= 2), "split mode needs two slots per stream");
   constexpr int kSlotK = kSlotBytes / kCtas;            // bytes of a slot held by one CTA
   const uint32_t rank = (kCtas == 2) ? cluster_ctarank() : 0u;
   const int unit0 = (kCtas == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work unit of this CTA (pair)
@@ -389,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   constexpr int kNumGemms = kBwd ? kNumGemmsBwd : (kSigmaOnly ? 8 : kNumGemmsFwd);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kRingK; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 2); mbar_init(bar_pfull(s), 1); }
+    for (int s = 0; s < kRingK; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), kSplit ? 1 : 2); mbar_init(bar_pfull(s), 1); }
     for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), (kShared ? 256 : 128) / kArriveLanes * kCtas); mbar_init(bar_acc(t), 1); }
     mbar_init(bar_skew, 1);
     fence_mbar_init();
@@ -424,11 +458,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 
   if (warp == 0) {
     // ================= weight producer =================
-    if (lane == 0) {
+    // shared stream: lane 0 fills the whole ring; split mode: lane t fills tile t's half-ring
+    if (lane < (kSplit ? 2 : 1)) {
+      const uint32_t base = kSplit ? (uint32_t)lane * kRingT : 0u;
       uint32_t g = 0;
       for (int unit = unit0; unit < num_units; unit += unit_step) {
         for (int i = 0; i < nslots; ++i, ++g) {
-          const uint32_t s = g % kRingK, ph = (g / kRingK) & 1;
+          const uint32_t s = base + g % kRingT, ph = (g / kRingT) & 1;
           const uint2 rec = *reinterpret_cast<const uint2*>(&c_slots[slot0 + i]);      // goff, bytes
           const uint32_t bytes = rec.y / kCtas;          // pair mode: this CTA's N-half of the slot
           mbar_wait(bar_empty(s), ph ^ 1, 100 + (int)s);
@@ -443,14 +479,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
     if (kCtas == 2 && rank != 0) {
       // peer CTA of a pair: its issuer warps do not issue; warp 1 relays "my half of slot s landed"
       // to the leader, whose MMAs read both halves.
-      if (warp == 1) {
-        uint32_t s = 0, ph = 0;
+      if (warp == 1 || kSplit) {                       // split mode: warp 1 + t relays tile t's stream
+        const uint32_t s_lo = kSplit ? (uint32_t)(warp - 1) * kRingT : 0u, s_hi = s_lo + kRingT;
+        uint32_t s = s_lo, ph = 0;
         for (int unit = unit0; unit < num_units; unit += unit_step) {
           for (int i = 0; i < nslots; ++i) {
             mbar_wait(bar_full(s), ph, 250 + (int)s);
             if (lane == 0) mbar_arrive_cluster(mapa(bar_pfull(s), 0));
             __syncwarp();
-            if (++s == kRingK) { s = 0; ph ^= 1; }
+            if (++s == s_hi) { s = s_lo; ph ^= 1; }
           }
         }
       }
@@ -467,8 +504,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
       const uint32_t b_lo0 = ((sbase + kOffRing) >> 4) | (1u << 16);
       const uint32_t d_tmem = tmem_base + (uint32_t)t * 256;
       constexpr uint32_t kIdesc256 = make_idesc_bf16(kTileM * kCtas, 256), kIdesc128 = make_idesc_bf16(kTileM * kCtas, 128);
-      uint32_t s = 0, ph = 0, act_ph = 0;
-      if (t == 1) mbar_wait(bar_skew, 0, 500);            // one-shot start offset behind tile A
+      const uint32_t s_lo = kSplit ? (uint32_t)t * kRingT : 0u, s_hi = s_lo + kRingT;
+      uint32_t s = s_lo, ph = 0, act_ph = 0;
+      // one-shot start offset behind tile A: kSkew slots (shared stream), or -- split mode -- until tile A's
+      // first epilogue has finished, i.e. half a period of the (now independent) per-tile chains
+      if (t == 1) mbar_wait(bar_skew, 0, 500);
       for (int unit = unit0; unit < num_units; unit += unit_step) {
         for (int i = 0; i < nslots; ++i) {
           const uint4 rec = *reinterpret_cast<const uint4*>(&c_slots[slot0 + i]);
@@ -483,7 +523,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 #ifdef NERF_DBG_TIMING
           const long long i1_ = clock64();
 #endif
-          if (fl & kFlagFirst) { mbar_wait(bar_act(t), act_ph, 300 + t); act_ph ^= 1; }
+          if (fl & kFlagFirst) {
+            TRACE(t, lane == 0 && unit == unit0 + 2 * unit_step, 1);       // layer start: weights of the first slot are there
+            mbar_wait(bar_act(t), act_ph, 300 + t); act_ph ^= 1;
+            TRACE(t, lane == 0 && unit == unit0 + 2 * unit_step, 2);       // activations ready
+          }
           tc_fence_after();
 #ifdef NERF_DBG_TIMING
           if (blockIdx.x == 0 && warp == 1 && lane == 0) {
@@ -514,10 +558,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
               tc_commit(bar_empty(s));                      // slot is free once both issuers' MMAs on it retired
               if (fl & kFlagLast) tc_commit(bar_acc(t));
             }
-            if (t == 0 && i == kSkew - 1 && unit == unit0) mbar_arrive(bar_skew);
+            if (!kSplit && t == 0 && i == kSkew - 1 && unit == unit0) mbar_arrive(bar_skew);
           }
           __syncwarp();
-          if (++s == kRingK) { s = 0; ph ^= 1; }
+          if (fl & kFlagLast) TRACE(t, lane == 0 && unit == unit0 + 2 * unit_step, 3);   // last MMA of the layer issued + committed
+          if (++s == s_hi) { s = s_lo; ph ^= 1; }
         }
       }
     }
@@ -568,22 +613,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
     };
     uint32_t acc_ph = 0u;                             // bit t = phase of bar_acc(t)
     const int64_t ntiles = a.Mp / kTileM;
-    // cross-warp scratch for the head partial sums (forward, last layer): the 4 KB of tile A's x-tile
-    // that hold rows 32q..32q+31 -- no MMA reads them after layer 5, warp (q,1) writes, warp (q,0)
-    // reads and is also the next to overwrite them (its prologue rows)
-    float4* xchg = reinterpret_cast<float4*>(smem + kOffX + q * 4096);
+    // cross-warp scratch for the head partial sums (forward, last layer of tile t): 512 B per lane quadrant in
+    // feature block 3 of tile t's OWN activation tile -- its last reader (the MMAs of the last layer) has
+    // completed when the accumulator barrier fires, the save mode stages hv / dir_enc in blocks 0-2 only, and the
+    // next writer (tile t's layer-0 epilogue of the next unit) needs tile t's next "activations ready" phase,
+    // which every thread joins only after it has read the scratch.
+    // (Not the x-tile: with NERF_TC_PIPE_PROLOGUE it already holds the next unit's encoding by then.)
+    auto xchg_of = [&](int t) { return reinterpret_cast<float4*>(smem + kOffAct + t * kActBytes + 3 * 16384 + q * 1024); };
     for (int unit = unit0; unit < num_units; unit += unit_step) {
       const int64_t tile0 = ((int64_t)unit * kCtas + rank) * 2;
+#ifdef NERF_DBG_TRACE
+      const int tw = (warp == kFirstComputeWarp) ? 2 : 3;
+      const bool tr_ok = (warp == kFirstComputeWarp || warp == kFirstComputeWarp + 4) && lane == 0 && unit == unit0 + 2 * unit_step;
+#endif
       if constexpr (!kBwd) {
         // ------------------------------ forward ------------------------------
-        {                                                  // prologue of the own tile
+        uint8_t* xt_own = smem + kOffX + h * kXBytes;
+        // inference kernels only: in the save-mode kernel the compute warps are the bottleneck and it measured slower (0.352 vs 0.346 ms)
+        constexpr bool kPipe = (NERF_TC_PIPE_PROLOGUE != 0) && !kSave;
+        {                                                  // prologue of the own tile (pipelined mode: first unit only)
           const int64_t row = (tile0 + h) * kTileM + m;
-          uint8_t* xt = smem + kOffX + h * kXBytes;
-          if (kShared) act_arrive(1 - h);                  // nothing to write for the other tile
-          fwd_prologue(a, row, m, xt);
-          fence_proxy_async();
-          act_arrive(h);
-          if (kSave) store_blocks(a.xenc_img + (tile0 + h) * 16384, 0, xt, 0, 1);
+          // (pipelined mode, later units: the x-tile was written under the previous unit's layer-6 wait and the
+          //  arrives were made right after each tile's last epilogue, so tile A's layer 0 runs under tile B's
+          //  last epilogue)
+          if (!kPipe || unit == unit0) {
+            if (kShared) act_arrive(1 - h);                // nothing to write for the other tile
+            fwd_prologue(a, row, m, xt_own);
+            fence_proxy_async();
+            act_arrive(h);
+          }
+          if (kSave && (!kPipe || unit == unit0)) store_blocks(a.xenc_img + (tile0 + h) * 16384, 0, xt_own, 0, 1);
         }
         float sigma0 = 0.f, sigma1 = 0.f;                  // partial sigma head of (tile A / B, own column half)
         for (int g = 0; g < kNumGemms; ++g) {
@@ -599,6 +658,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             mbar_wait(bar_acc(t), (acc_ph >> t) & 1u, 400 + t);
             acc_ph ^= 1u << t;
             tc_fence_after();
+            TRACE(tw, tr_ok, 4 + 8 * t);
             DBG_T(t1_);
             DBG_ACC(0, t1_ - t0_);
             if (kSigmaOnly && g == 7) {
@@ -613,10 +673,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
                 for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), head[c0 + j], sigma);
               }
               tc_fence_before();
-              if (h == 1) xchg[t * 32 + lane] = make_float4(0.f, 0.f, 0.f, sigma);
+              float4* xchg = xchg_of(t);
+              if (h == 1) xchg[lane] = make_float4(0.f, 0.f, 0.f, sigma);
               named_bar_sync(1, 256);
               if (h == 0 && valid)
-                *reinterpret_cast<float4*>(a.out + row * 4) = make_float4(0.f, 0.f, 0.f, sigma + xchg[t * 32 + lane].w + head[640]);
+                *reinterpret_cast<float4*>(a.out + row * 4) = make_float4(0.f, 0.f, 0.f, sigma + xchg[lane].w + head[640]);
+              if (kPipe && unit + unit_step < num_units) act_arrive(t);     // next unit's layer 0 of this tile may start
             } else if (g < 9) {
 #pragma unroll 1
              for (int ch = ch_lo; ch < ch_hi; ++ch) {
@@ -667,6 +729,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
               tc_fence_before();
               fence_proxy_async();
               act_arrive(t);
+              if (kSplit && g == 0 && t == 0 && unit == unit0 && warp == kFirstComputeWarp && lane == 0) mbar_arrive(bar_skew);   // start tile B's chain
+              TRACE(tw, tr_ok, 5 + 8 * t);
               DBG_T(t2_);
               DBG_ACC(1, t2_ - t1_);
               DBG_ACC(3, 1);
@@ -675,6 +739,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 #pragma unroll 1
                 for (int ch = ch_lo; ch < ch_hi; ++ch)
                   store_blocks(a.act_img + ((int64_t)g * ntiles + tile) * 65536, 2 * ch, at, 2 * ch, 2);
+                TRACE(tw, tr_ok, 6 + 8 * t);
                 DBG_T(t3_);
                 DBG_ACC(2, t3_ - t2_);
               }
@@ -728,15 +793,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
               tc_fence_before();
               // shared mode: combine the two column halves of the heads: half 1 hands its partial sums to half 0
               if (kShared) {
-                if (h == 1) xchg[t * 32 + lane] = make_float4(o0, o1, o2, sigma);
+                if (h == 1) xchg_of(t)[lane] = make_float4(o0, o1, o2, sigma);
                 named_bar_sync(1, 256);
               }
               if (!kShared || h == 0) {
-                const float4 p = kShared ? xchg[t * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 p = kShared ? xchg_of(t)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid)
                   *reinterpret_cast<float4*>(a.out + row * 4) =
                       make_float4(o0 + p.x + head[641], o1 + p.y + head[642], o2 + p.z + head[643], sigma + p.w + head[640]);
               }
+              if (kPipe && unit + unit_step < num_units) act_arrive(t);     // next unit's layer 0 of this tile may start
               if (kSave) {
 #pragma unroll 1
                 for (int ch = ch_lo; ch < ch_hi; ++ch) store_blocks(a.hv_img + tile * 32768, ch, at, 2 * ch, 1);
@@ -758,6 +824,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
                 }
               }
             }
+          }
+          if (kPipe && g == 5 && unit + unit_step < num_units) {
+            // layer 5 was the x-tile's last reader (its MMAs completed before the accumulator barrier fired):
+            // encode the next unit's points now, under the wait for the layer-6 accumulators
+            const int64_t tile0n = ((int64_t)(unit + unit_step) * kCtas + rank) * 2;
+            fwd_prologue(a, (tile0n + h) * kTileM + m, m, xt_own);
+            fence_proxy_async();
+            if (kSave) store_blocks(a.xenc_img + (tile0n + h) * 16384, 0, xt_own, 0, 1);
           }
         }
       } else {
@@ -825,6 +899,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             mbar_wait(bar_acc(t), (acc_ph >> t) & 1u, 400 + t);
             acc_ph ^= 1u << t;
             tc_fence_after();
+            TRACE(tw, tr_ok, 4 + 8 * t);
             DBG_T(t1_);
             DBG_ACC(0, t1_ - t0_);
             // one 32-column chunk: (+ sigma term) -> ReLU mask -> bf16 -> swizzled store
@@ -868,12 +943,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             tc_fence_before();
             fence_proxy_async();
             if (g < kNumGemms - 1) act_arrive(t);
+            if (kSplit && g == 0 && t == 0 && unit == unit0 && warp == kFirstComputeWarp && lane == 0) mbar_arrive(bar_skew);   // start tile B's chain
+            TRACE(tw, tr_ok, 5 + 8 * t);
             DBG_T(t2_);
             DBG_ACC(1, t2_ - t1_);
             DBG_ACC(3, 1);
 #pragma unroll 1
             for (int ch = ch_lo; ch < ch_hi; ++ch)
               store_blocks(a.dpre_img + ((int64_t)dst * ntiles + tile) * 65536, 2 * ch, at, 2 * ch, 2);
+            TRACE(tw, tr_ok, 6 + 8 * t);
             DBG_T(t3_);
             DBG_ACC(2, t3_ - t2_);
           }
@@ -889,6 +967,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
     printf("DBG issuer A (CTA 0): per slot: weight wait %.0f clk, activation wait %.0f clk (x slots per layer ~8.7), slots=%.0f\n",
            g_dbg_clk[4] / (double)g_dbg_clk[6], g_dbg_clk[5] / (double)g_dbg_clk[6], (double)g_dbg_clk[6]);
     g_dbg_clk[0] = g_dbg_clk[1] = g_dbg_clk[2] = g_dbg_clk[3] = g_dbg_clk[4] = g_dbg_clk[5] = g_dbg_clk[6] = 0;
+  }
+#endif
+#ifdef NERF_DBG_TRACE
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && g_trace_n[0] > 0) {
+    long long t0 = g_trace[0][0] >> 4;
+    printf("TRACE kBwd=%d kSave=%d kSplit=%d kShared=%d\n", (int)kBwd, (int)kSave, (int)kSplit, (int)kShared);
+    for (int w = 0; w < 4; ++w) {
+      for (int i = 0; i < g_trace_n[w]; ++i) printf("T %d %d %lld\n", w, (int)(g_trace[w][i] & 15), (g_trace[w][i] >> 4) - t0);
+      g_trace_n[w] = 0;
+    }
   }
 #endif
   __syncthreads();
