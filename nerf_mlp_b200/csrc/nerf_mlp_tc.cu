@@ -59,6 +59,15 @@ constexpr int kArriveLanes = NERF_TC_ARRIVE_LANES;
 // for the layer-6 accumulators of the current one (the x-tile's last reader is layer 5), so the unit boundary costs
 // one ordinary layer transition instead of  drain + last epilogue + prologue  (timeline: 6.6k clk of idle tensor
 // pipe per unit of 62k in the inference kernel, 13k of ~100k in the save-mode kernel).
+// Pair mode: the peer's "my half of slot s landed" relay arrives directly on the leader's full(s) barrier (count 2)
+// instead of a second barrier, so the issue loop makes one barrier wait per slot instead of two.
+#ifndef NERF_TC_RELAY_FULL
+#define NERF_TC_RELAY_FULL 1
+#endif
+// The issuer warps' barrier polls are made by lane 0 alone (then __syncwarp) instead of by all 32 lanes.
+#ifndef NERF_TC_POLL_LANE0
+#define NERF_TC_POLL_LANE0 0                      // measured: 70.6 vs 84.4 % of peak -- the extra __syncwarp per slot costs far more than the 31 polls
+#endif
 #ifndef NERF_TC_PIPE_PROLOGUE
 #define NERF_TC_PIPE_PROLOGUE 1
 #endif
@@ -157,10 +166,11 @@ static const Schedule& schedule() {
             sl.goff = goff;
             sl.bytes = (uint32_t)g.n * 32 * nk;
             sl.a_add = (uint32_t)((k0 >> 6) * 16384 + ((k0 & 63) >> 4) * 32) >> 4;
-            sl.flags = (uint32_t)p.kind | (nk == 2 ? kFlagNk2 : 0) | (g.n == 128 ? kFlagN128 : 0);
+            if (nk == 3) { fprintf(stderr, "nerf_b200: schedule: K tail of 3 steps is not supported\n"); abort(); }
+            sl.flags = (uint32_t)p.kind | (nk == 2 ? kFlagNk2 : 0) | (nk == 4 ? kFlagNk4 : 0) | (g.n == 128 ? kFlagN128 : 0);
             PackSlot ps{};
             ps.goff = goff; ps.w_base = p.w0 + k0 * p.ks; ps.n_stride = p.ns; ps.k_stride = p.ks;
-            ps.kvalid = p.kvalid - k0; ps.n = g.n; ps.nk = nk; ps.sw = (nk == 2) ? 64 : 32;
+            ps.kvalid = p.kvalid - k0; ps.n = g.n; ps.nk = nk; ps.sw = (nk == 4) ? 128 : (nk == 2) ? 64 : 32;
             s.slots.push_back(sl); s.pack.push_back(ps);
             goff += kSlotBytes;          // fixed stride keeps every slot 8 KB aligned in the image
           }
@@ -226,7 +236,7 @@ __global__ void pack_kernel(const float* __restrict__ params, uint8_t* __restric
     } else if (kk < ps.kvalid) {
       v = params[ps.w_base + (int64_t)n * ps.n_stride + (int64_t)kk * ps.k_stride];
     }
-    const uint32_t off = (ps.sw == 64) ? sw64_off(n, kk) : sw32_off(n, kk);
+    const uint32_t off = (ps.sw == 128) ? sw128_off(n, kk) : (ps.sw == 64) ? sw64_off(n, kk) : sw32_off(n, kk);
     *reinterpret_cast<__nv_bfloat16*>(packed + ps.goff + off) = __float2bfloat16_rn(v);
   }
 }
@@ -423,7 +433,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   constexpr int kNumGemms = kBwd ? kNumGemmsBwd : (kSigmaOnly ? 8 : kNumGemmsFwd);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kRingK; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), kSplit ? 1 : 2); mbar_init(bar_pfull(s), 1); }
+    constexpr bool kRelayFull = NERF_TC_RELAY_FULL != 0;
+    for (int s = 0; s < kRingK; ++s) {
+      mbar_init(bar_full(s), (kCtas == 2 && kRelayFull && rank == 0) ? 2 : 1);      // leader: own bytes + the peer's relay
+      mbar_init(bar_empty(s), kSplit ? 1 : 2);
+      mbar_init(bar_pfull(s), 1);
+    }
     for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), (kShared ? 256 : 128) / kArriveLanes * kCtas); mbar_init(bar_acc(t), 1); }
     mbar_init(bar_skew, 1);
     fence_mbar_init();
@@ -485,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
         for (int unit = unit0; unit < num_units; unit += unit_step) {
           for (int i = 0; i < nslots; ++i) {
             mbar_wait(bar_full(s), ph, 250 + (int)s);
-            if (lane == 0) mbar_arrive_cluster(mapa(bar_pfull(s), 0));
+            if (lane == 0) mbar_arrive_cluster(mapa((NERF_TC_RELAY_FULL != 0) ? bar_full(s) : bar_pfull(s), 0));
             __syncwarp();
             if (++s == s_hi) { s = s_lo; ph ^= 1; }
           }
@@ -516,18 +531,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 #ifdef NERF_DBG_TIMING
           const long long i0_ = clock64();
 #endif
-          mbar_wait(bar_full(s), ph, 200 + (int)s);
           // plain (cta-scope) waits, as CUTLASS's 2-SM pipelines do: the remote arrivals are
           // release.cluster and the data they publish is consumed by the async proxy (the MMA)
-          if (kCtas == 2) mbar_wait(bar_pfull(s), ph, 220 + (int)s);
+          if (NERF_TC_POLL_LANE0 == 0 || lane == 0) {
+            mbar_wait(bar_full(s), ph, 200 + (int)s);
+            if (kCtas == 2 && NERF_TC_RELAY_FULL == 0) mbar_wait(bar_pfull(s), ph, 220 + (int)s);
+          }
 #ifdef NERF_DBG_TIMING
           const long long i1_ = clock64();
 #endif
           if (fl & kFlagFirst) {
             TRACE(t, lane == 0 && unit == unit0 + 2 * unit_step, 1);       // layer start: weights of the first slot are there
-            mbar_wait(bar_act(t), act_ph, 300 + t); act_ph ^= 1;
+            if (NERF_TC_POLL_LANE0 == 0 || lane == 0) mbar_wait(bar_act(t), act_ph, 300 + t);
+            act_ph ^= 1;
             TRACE(t, lane == 0 && unit == unit0 + 2 * unit_step, 2);       // activations ready
           }
+          if (NERF_TC_POLL_LANE0 != 0) __syncwarp();                       // lane 0's acquire is ordered before the elected lane's issue
           tc_fence_after();
 #ifdef NERF_DBG_TIMING
           if (blockIdx.x == 0 && warp == 1 && lane == 0) {
@@ -540,21 +559,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           const uint32_t a_lo = (kind == A_X ? a_lo_x : (kind == A_ACT ? a_lo_act : a_lo_ones)) + a_add;
           const uint32_t a_hi = (kind == A_ONES) ? kHiOnes : kHiSw128;
           const uint32_t b_lo = b_lo0 + s * (kSlotK >> 4);
-          const uint32_t b_hi = (fl & kFlagNk2) ? kHiSw64 : kHiSw32;
+          const uint32_t b_hi = (fl & kFlagNk4) ? kHiSw128 : (fl & kFlagNk2) ? kHiSw64 : kHiSw32;
           const uint32_t idesc = (fl & kFlagN128) ? kIdesc128 : kIdesc256;
           if (elect_one()) {
             if (kCtas == 2) {
               mma_bf16_ss_2cta(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
                                (fl & kFlagFirst) ? 0u : 1u);
-              if (fl & kFlagNk2)
+              if (fl & (kFlagNk2 | kFlagNk4))
                 mma_bf16_ss_2cta(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2), ((uint64_t)b_hi << 32) | (b_lo + 2), idesc, 1u);
+              if (fl & kFlagNk4) {
+                mma_bf16_ss_2cta(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 4), ((uint64_t)b_hi << 32) | (b_lo + 4), idesc, 1u);
+                mma_bf16_ss_2cta(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 6), ((uint64_t)b_hi << 32) | (b_lo + 6), idesc, 1u);
+              }
               tc_commit_mc2(bar_empty(s), 3);               // both CTAs' producers may refill the slot
               if (fl & kFlagLast) tc_commit_mc2(bar_acc(t), 3);   // both CTAs' epilogues may read their accumulators
             } else {
               mma_bf16_ss(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
                           (fl & kFlagFirst) ? 0u : 1u);
-              if (fl & kFlagNk2)
+              if (fl & (kFlagNk2 | kFlagNk4))
                 mma_bf16_ss(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2), ((uint64_t)b_hi << 32) | (b_lo + 2), idesc, 1u);
+              if (fl & kFlagNk4) {
+                mma_bf16_ss(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 4), ((uint64_t)b_hi << 32) | (b_lo + 4), idesc, 1u);
+                mma_bf16_ss(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 6), ((uint64_t)b_hi << 32) | (b_lo + 6), idesc, 1u);
+              }
               tc_commit(bar_empty(s));                      // slot is free once both issuers' MMAs on it retired
               if (fl & kFlagLast) tc_commit(bar_acc(t));
             }

@@ -19,7 +19,7 @@ namespace nerf {
 constexpr int kNK = NERF_TC_NK;
 constexpr int kRing = NERF_TC_RING;
 constexpr int kSkew = NERF_TC_SKEW;
-static_assert(kNK == 1 || kNK == 2, "slot = 1 or 2 K-steps");
+static_assert(kNK == 1 || kNK == 2 || kNK == 4, "slot = 1, 2 or 4 K-steps");
 static_assert(kSkew >= 1 && kSkew + 1 < 2 * kRing, "ring must hold the skew plus at least one prefetch slot");
 constexpr int kSlotBytes = 8192 * kNK;            // 256 rows x 32 B x NK
 constexpr int kTileM = 128;
@@ -45,9 +45,9 @@ enum AKind : uint32_t { A_X = 0, A_ACT = 1, A_ONES = 2 };
 struct Slot {            // consumed by the kernels: one 16-byte constant-bank load per slot
   uint32_t goff, bytes;
   uint32_t a_add;        // (byte offset of the first K-step inside the A tile) >> 4
-  uint32_t flags;        // bits 0-1 a_kind | 2 nk==2 | 3 first | 4 last | 5 N==128
+  uint32_t flags;        // bits 0-1 a_kind | 2 nk==2 | 3 first | 4 last | 5 N==128 | 6 nk==4
 };
-constexpr uint32_t kFlagNk2 = 4, kFlagFirst = 8, kFlagLast = 16, kFlagN128 = 32;
+constexpr uint32_t kFlagNk2 = 4, kFlagFirst = 8, kFlagLast = 16, kFlagN128 = 32, kFlagNk4 = 64;
 struct PackSlot {        // consumed by the pack kernel: value(n,kk) = params[w_base + n*n_stride + kk*k_stride]
   uint32_t goff;
   int32_t w_base, n_stride, k_stride, kvalid, b_off, n, nk, sw, is_bias;
