@@ -48,9 +48,9 @@ FLOP_PER_ROW_BWD = 2302208
 # layers + d_bottleneck (9 x 512 B) + d_hv (256 B); X = h0..h7 + bottleneck (9 x 512 B) + x_enc (128 B) + dir_enc (128 B)
 WGRAD_ALG_BYTES_PER_ROW = 9 * 512 + 256 + 9 * 512 + 128 + 128
 # measured DRAM traffic (ncu dram__bytes_read.sum + dram__bytes_write.sum), see profiles/
-NCU_BYTES_PER_ROW_FWD_SAVE = 5150.0      # 1.0126 GB on the 196 608-row save-mode launch
-NCU_BYTES_PER_ROW_WGRAD = 10444.0        # 2.0533 GB on the same rows
-NCU_BYTES_FWD_INFER_3145728 = 25.58e6    # whole 3 145 728-row inference launch (22.73 MB read + 2.85 MB written)
+NCU_BYTES_PER_ROW_FWD_SAVE = 5162.0      # 1.0149 GB on the 196 608-row save-mode launch
+NCU_BYTES_PER_ROW_WGRAD = 10442.0        # 2.0530 GB on the same rows
+NCU_BYTES_FWD_INFER_3145728 = 27.07e6    # whole 3 145 728-row inference launch (22.71 MB read + 4.36 MB written)
 N_SAMPLES, N_IMPORTANCE = 64, 128
 
 
@@ -534,15 +534,15 @@ def main():
                        "frac_of_sustained": (achieved / pk["bf16_tflops_sustained"]) if pk.get("bf16_tflops_sustained") else None,
                        "rows_per_launch": rows_max, "flop_per_row": FLOP_PER_ROW_FWD, "avg_launch_ms": avg_ms,
                        "share_of_step": mlp_ms_per_step / step_ms, "traffic": None}
-    # DRAM traffic per launch from the committed ncu --set full captures (profiles/r01c_*_ncu_summary.csv), per row x rows
+    # DRAM traffic per launch from the committed ncu --set full captures (profiles/r01d_*_ncu_summary.csv), per row x rows
     if args.precision == "bf16":
         if args.workload == "render" and rows_max == 3145728:
             roofline_tensor["traffic"] = NCU_BYTES_FWD_INFER_3145728 if (N_SAMPLES, N_IMPORTANCE) == (64, 128) else None
-            roofline_tensor["traffic_source"] = "ncu dram__bytes_read+write, profiles/r01c_mlp_fwd_ncu_summary.csv"
+            roofline_tensor["traffic_source"] = "ncu dram__bytes_read+write, profiles/r01d_mlp_fwd_ncu_summary.csv"
         elif args.workload == "train":
             roofline_tensor["traffic"] = NCU_BYTES_PER_ROW_FWD_SAVE * rows_max
             roofline_tensor["traffic_source"] = ("ncu dram__bytes_read+write per row of the 196 608-row save-mode launch "
-                                                 "(profiles/r01c_train_step_ncu_summary.csv) x rows of this launch")
+                                                 "(profiles/r01d_train_step_ncu_summary.csv) x rows of this launch")
     roofline = roofline_tensor
     if stage_acc is not None and args.precision == "bf16" and "mlp_bwd_wgrad" in stage_acc:
         wg_ms = stage_acc["mlp_bwd_wgrad"]
@@ -553,7 +553,7 @@ def main():
                     "rows_per_launch": rows_max, "bytes_per_row": WGRAD_ALG_BYTES_PER_ROW, "avg_launch_ms": wg_ms,
                     "share_of_step": wg_ms / step_ms,
                     "traffic": NCU_BYTES_PER_ROW_WGRAD * rows_max,
-                    "traffic_source": "ncu dram__bytes_read+write per row (profiles/r01c_train_step_ncu_summary.csv) x rows"}
+                    "traffic_source": "ncu dram__bytes_read+write per row (profiles/r01d_train_step_ncu_summary.csv) x rows"}
 
     line = {"metric": f"{args.workload}_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload == "train" else "strong",
