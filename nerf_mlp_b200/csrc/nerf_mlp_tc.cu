@@ -71,6 +71,9 @@ constexpr int kArriveLanes = NERF_TC_ARRIVE_LANES;
 #ifndef NERF_TC_PIPE_PROLOGUE
 #define NERF_TC_PIPE_PROLOGUE 1
 #endif
+#ifndef NERF_TC_VB_PREFETCH
+#define NERF_TC_VB_PREFETCH 0                     // L1 prefetch of the view-bias row under the view layer's accumulator wait (measured: no change, 84.9 % both)
+#endif
 #ifndef NERF_TC_SHARED_TRAIN
 #define NERF_TC_SHARED_TRAIN 0                    // 1: the save / dgrad kernels share every epilogue among all eight warps too
 #endif
@@ -682,6 +685,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             uint8_t* at = smem + kOffAct + t * kActBytes;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256;
             DBG_T(t0_);
+            if (NERF_TC_VB_PREFETCH != 0 && !kSigmaOnly && g == 9) {
+              // the view-layer epilogue adds this row's 512-byte view-bias vector (one per ray, L2-resident): pull its
+              // four lines into L1 while waiting for the accumulator instead of paying the L2 latency twice inside the
+              // epilogue (the timeline showed 2 800 clk per view epilogue against ~1 050 for a trunk layer)
+              const char* vbp = reinterpret_cast<const char*>(a.vb + ((valid ? row : (a.M - 1)) / a.vb_div) * 128);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(vbp + 128 * i));
+            }
             mbar_wait(bar_acc(t), (acc_ph >> t) & 1u, 400 + t);
             acc_ph ^= 1u << t;
             tc_fence_after();
