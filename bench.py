@@ -527,10 +527,18 @@ def main():
         mlp_ms_per_step = sum(a.elapsed_time(b) for _, a, b in mlp_events) / K
     achieved = rows_max * FLOP_PER_ROW_FWD / (avg_ms * 1e-3) / 1e12
     step_ms = sum(ms_steps) / K
+    # Denominator (task contract): the BURST matmul figure for a kernel timed in a short region, the SUSTAINED one for a
+    # kernel timed inside a long back-to-back region (>= 0.2 s of device time: the 200-step training run and the 800x800
+    # render sit in the power cap, as the 4 s sustained matmul measurement does).  Both fractions are always reported.
+    long_run = (step_ms * K * 1e-3) >= 0.2 and pk.get("bf16_tflops_sustained")
+    tc_peak = pk["bf16_tflops_sustained"] if long_run else pk["bf16_tflops"]
+    tc_peak_kind = (", sustained bf16 matmul (kernel timed inside a %.2f s back-to-back region)" % (step_ms * K * 1e-3)) if long_run \
+        else ", burst bf16 matmul (short timed region)"
     roofline_tensor = {"kernel": ("mlp_tc_kernel<fwd" + (", save" if args.workload == "train" else "") + "> (fused PE + 8x256 MLP + heads), fine pass")
                        if args.precision == "bf16" else "fp32 check-mode SGEMM chain",
-                       "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                       "frac": achieved / pk["bf16_tflops"], "peak_source": pk["source"] + ", burst bf16 matmul",
+                       "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+                       "frac": achieved / tc_peak, "peak_source": pk["source"] + tc_peak_kind,
+                       "frac_of_burst": achieved / pk["bf16_tflops"],
                        "frac_of_sustained": (achieved / pk["bf16_tflops_sustained"]) if pk.get("bf16_tflops_sustained") else None,
                        "rows_per_launch": rows_max, "flop_per_row": FLOP_PER_ROW_FWD, "avg_launch_ms": avg_ms,
                        "share_of_step": mlp_ms_per_step / step_ms, "traffic": None}
