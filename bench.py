@@ -269,6 +269,31 @@ def run_reference(args):
     emit(line)
 
 
+# ------------------------------------------------------------------------------------------------
+# Synthetic inputs of the product arm.  Kept here so that the timed product path never imports
+# anything under oracle/ (the oracle is only executed by the CPU legs above and by the torch-eager baseline).
+# ------------------------------------------------------------------------------------------------
+def synthetic_rays(n, seed):
+    """i.i.d. origins ~ N((0,0,4), 0.1^2), non-unit directions ~ N(0,I) with d_z <- -|d_z| - 1 (exercises the |d| scaling)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    o = (np.array([0, 0, 4], np.float32) + 0.1 * rng.standard_normal((n, 3))).astype(np.float32)
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    d[:, 2] = -np.abs(d[:, 2]) - 1.0
+    return o, d
+
+
+def synthetic_pinhole_rays(H, W, fov=0.6911):
+    """Pinhole camera at (0,0,4), identity rotation, looking down -z: the view scripts/render_example.py:245-250 builds."""
+    import math
+    import numpy as np
+    focal = 0.5 * W / math.tan(0.5 * fov)
+    i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32), indexing="xy")
+    d = np.stack([(i - W * 0.5) / focal, -(j - H * 0.5) / focal, -np.ones_like(i)], -1).reshape(-1, 3).astype(np.float32)
+    o = np.broadcast_to(np.array([0, 0, 4], np.float32), d.shape).copy()
+    return o, d, focal
+
+
 def workload_config(args, rays_override=None):
     if args.workload == "train":
         rays = rays_override or args.rays or 1024
@@ -299,7 +324,6 @@ def main():
     import torch.distributed as td
     import nerf_mlp_b200 as nb
     from nerf_mlp_b200 import ops
-    from oracle import nerf_oracle as O
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -343,7 +367,7 @@ def main():
 
     if args.workload == "train":
         rays = args.rays or 1024
-        o_np, d_np = O.random_rays(rays, 100 + rank)
+        o_np, d_np = synthetic_rays(rays, 100 + rank)
         tgt_np = np.random.default_rng(200 + rank).uniform(0, 1, (rays, 3)).astype(np.float32)
         o, d, tgt = (torch.from_numpy(a).to(dev) for a in (o_np, d_np, tgt_np))
         renderer = nb.NeRFRenderer(model, dev, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=1.0,
@@ -391,7 +415,7 @@ def main():
             Himg, Wimg = total, 1
         else:
             Wimg = Himg
-        o_np, d_np, focal = O.pinhole_rays(Himg, Wimg) if Wimg > 1 else (*O.random_rays(total, 1), 1.0)
+        o_np, d_np, focal = synthetic_pinhole_rays(Himg, Wimg) if Wimg > 1 else (*synthetic_rays(total, 1), 1.0)
         lo, hi = nb.dist.shard_range(total, rank, world)
         o, d = torch.from_numpy(o_np[lo:hi]).to(dev), torch.from_numpy(d_np[lo:hi]).to(dev)
         renderer = nb.NeRFRenderer(model, dev, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=0.0,

@@ -276,3 +276,26 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert "torch CPU restatement" in d["cpu_baseline"]["sample"] and d["config"]["rays_per_gpu"] == 128
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_oracle_is_only_reachable_from_checker_and_baseline_code():
+    """The oracle is test infrastructure: nothing under nerf_mlp_b200/ may import it, and bench.py may execute it only
+    in its CPU legs (cpu_step_fn -> cpu_baseline / --impl reference) and in the separately reported torch-eager
+    baseline -- never inside main()'s product path."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "nerf_mlp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.lower() or f.endswith((".cu", ".cuh")) and "import" not in txt, os.path.join(dirpath, f)
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    allowed = {"cpu_step_fn", "time_torch_eager_gpu"}
+    for node in tree.body:
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            mod = getattr(node, "module", None) or ""
+            assert not mod.startswith("oracle") and all(not a.name.startswith("oracle") for a in node.names)
+        if isinstance(node, ast.FunctionDef):
+            uses = [n for n in ast.walk(node) if isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle")]
+            assert not uses or node.name in allowed, node.name
