@@ -70,7 +70,7 @@ def test_numpy_checker_tracks_torch_restatement(case):
     cdf_ref = torch.cat([torch.zeros(R, 1), torch.cumsum(torch.from_numpy(w + np.float32(1e-5)) /
                                                        torch.sum(torch.from_numpy(w + np.float32(1e-5)), -1, keepdim=True), -1)], -1)
     uu = np.broadcast_to(u, (R, N)) if u.ndim == 1 else u
-    ref_inds = torch.searchsorted(cdf_ref, torch.from_numpy(np.array(uu)), right=True).numpy()
+    ref_inds = torch.searchsorted(cdf_ref, torch.from_numpy(np.array(uu, order="C")), right=True).numpy()
     assert np.array_equal(O.searchsorted_right(cdf_ref.numpy(), uu), ref_inds)
 
 
@@ -114,3 +114,40 @@ def test_train_gradients_match_autograd_on_a_ragged_batch():
         a, b = grads[k].astype(np.float64), pt[k].grad.numpy().astype(np.float64)
         tol = 1e-3 if k.startswith("sigma_linear") else 2e-4
         assert np.linalg.norm(a - b) <= tol * np.linalg.norm(b) + 1e-12, (k, np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+# ---- property tests (hypothesis): resampling on degenerate pdfs ---------------------------------------------------
+from hypothesis import given, settings, strategies as st_  # noqa: E402
+
+
+def _torch_cdf(w):
+    tw = torch.from_numpy(w) + 1e-5
+    pdf = tw / torch.sum(tw, -1, keepdim=True)
+    return torch.cat([torch.zeros(w.shape[0], 1), torch.cumsum(pdf, -1)], -1)
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=st_.integers(0, 10_000), nbins=st_.integers(3, 70), nimp=st_.integers(1, 96),
+       kind=st_.sampled_from(["zeros", "spike", "uniform", "sparse", "huge"]), det=st_.booleans())
+def test_sample_pdf_on_degenerate_weights(seed, nbins, nimp, kind, det):
+    """All-zero weights, one spike, exactly uniform, mostly-zero and 1e6-scale weights; u on a grid that hits 0 and 1
+    exactly or random: given the reference's cdf bits the checker's indices are bit-exact and its samples within 2e-6;
+    with its own cdf the samples stay inside the bins and are monotone for sorted u."""
+    g = np.random.default_rng(seed)
+    R = 5
+    bins = np.sort(g.uniform(2, 6, (R, nbins)).astype(np.float32), -1)
+    w = {"zeros": np.zeros((R, nbins - 1)), "uniform": np.full((R, nbins - 1), 0.25),
+         "spike": np.eye(nbins - 1)[g.integers(0, nbins - 1, R)] * 3.0,
+         "sparse": g.uniform(0, 1, (R, nbins - 1)) * (g.uniform(0, 1, (R, nbins - 1)) < 0.15),
+         "huge": g.uniform(0, 1e6, (R, nbins - 1))}[kind].astype(np.float32)
+    u = np.linspace(0, 1, nimp, dtype=np.float32) if det else np.sort(g.uniform(0, 1, (R, nimp)).astype(np.float32), -1)
+    ref = T.sample_pdf(torch.from_numpy(bins), torch.from_numpy(w), torch.from_numpy(u)).numpy()
+    cdf_ref = _torch_cdf(w).numpy()
+    uu = np.broadcast_to(u, (R, nimp)) if u.ndim == 1 else u
+    inds_ref = torch.searchsorted(torch.from_numpy(cdf_ref), torch.from_numpy(np.array(uu, order="C")), right=True).numpy()
+    assert np.array_equal(O.searchsorted_right(cdf_ref, uu), inds_ref)
+    np.testing.assert_allclose(O.sample_pdf(bins, w, u, cdf=cdf_ref), ref, atol=2e-6, rtol=0)
+    own = O.sample_pdf(bins, w, u)
+    assert np.all(own >= bins[:, :1] - 1e-6) and np.all(own <= bins[:, -1:] + 1e-6)
+    assert np.all(np.diff(own, axis=-1) >= -2e-6)
+    assert np.all(np.isfinite(own)) and np.all(np.isfinite(ref))
