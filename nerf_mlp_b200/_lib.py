@@ -84,6 +84,14 @@ def ptr(t):
 
 
 def stream_ptr(device=None):
+    """Current torch stream of `device` as a cudaStream_t.  The library launches on the CALLING THREAD's current
+    device (its per-device kernel attributes and SM count follow cudaGetDevice), so tensors on another device must be
+    used under ``torch.cuda.device(...)``: refused here with a clear error instead of a failed or mis-sized launch."""
+    if device is not None:
+        idx = torch.device(device).index
+        if idx is not None and idx != torch.cuda.current_device():
+            raise RuntimeError(f"nerf_mlp_b200: tensors are on cuda:{idx} but the current device is "
+                               f"cuda:{torch.cuda.current_device()}; wrap the call in `with torch.cuda.device({idx}):`")
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

@@ -21,6 +21,20 @@ int cuda_fail(cudaError_t e, const char* what) {
   return (int)e > 0 ? (int)e : 1;
 }
 
+int current_device(DeviceProps* out) {
+  static DeviceProps cache[kMaxDevices];
+  static bool have[kMaxDevices] = {};
+  int dev = 0;
+  NERF_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < kMaxDevices && __atomic_load_n(&have[dev], __ATOMIC_ACQUIRE)) { *out = cache[dev]; return 0; }
+  cudaDeviceProp p;
+  NERF_CUDA(cudaGetDeviceProperties(&p, dev));
+  DeviceProps d{dev, p.major, p.minor, p.multiProcessorCount};
+  if (dev >= 0 && dev < kMaxDevices) { cache[dev] = d; __atomic_store_n(&have[dev], true, __ATOMIC_RELEASE); }
+  *out = d;
+  return 0;
+}
+
 }  // namespace nerf
 
 using namespace nerf;
@@ -30,12 +44,11 @@ extern "C" unsigned long long nerf_launch_count(void) { return __atomic_load_n(&
 extern "C" const char* nerf_version(void) { return "nerf_b200 0.1 (sm_100a)"; }
 
 extern "C" int nerf_device_info(int* sm, int* sm_count) {
-  int dev = 0;
-  NERF_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp p;
-  NERF_CUDA(cudaGetDeviceProperties(&p, dev));
-  if (sm) *sm = p.major * 10 + p.minor;
-  if (sm_count) *sm_count = p.multiProcessorCount;
+  DeviceProps p;
+  int rc = current_device(&p);
+  if (rc) return rc;
+  if (sm) *sm = p.sm_major * 10 + p.sm_minor;
+  if (sm_count) *sm_count = p.sm_count;
   return 0;
 }
 

@@ -52,6 +52,20 @@ int cuda_fail(cudaError_t e, const char* what);
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- per-device state ------------------------------------------------------------------------
+// Function attributes (cudaFuncSetAttribute), the SM count and the constant-memory schedules are
+// per DEVICE, not per process: one process may drive several GPUs.  `current_device`
+// returns the calling thread's device ordinal with its cached properties; `DeviceOnce` is a
+// one-time flag per device for "set this kernel's attributes once".
+constexpr int kMaxDevices = 64;
+struct DeviceProps { int ordinal, sm_major, sm_minor, sm_count; };
+int current_device(DeviceProps* out);
+struct DeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool needed(int dev) const { return dev < 0 || dev >= kMaxDevices || !done[dev]; }
+  void mark(int dev) { if (dev >= 0 && dev < kMaxDevices) done[dev] = true; }
+};
+
 // ---- device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -87,15 +87,9 @@ constexpr int kNumGemmsFwd = 10, kNumGemmsBwd = 9;
 // ---- shared memory map (bytes) ------------------------------------------------------------------
 constexpr int kOffAct = 0;                                   // 2 x [128 x 256] bf16, SW128 K-blocks of 64
 constexpr int kActBytes = 65536;
-#ifdef NERF_DBG_ALIAS_X   // timing experiment only (wrong results): x-tiles alias the activation tiles, ring takes their 32 KB
-constexpr int kOffX = kOffAct;
-constexpr int kXBytes = kActBytes;
-constexpr int kOffRing = kOffAct + 2 * kActBytes;
-#else
 constexpr int kOffX = kOffAct + 2 * kActBytes;               // 2 x [128 x 64] bf16, SW128
 constexpr int kXBytes = 16384;
 constexpr int kOffRing = kOffX + 2 * kXBytes;
-#endif
 constexpr int kOffOnes = kOffRing + kRing * kSlotBytes;      // [8 x 16] bf16, SW32; all 16 row groups alias it (SBO = 0)
 constexpr int kOnesBytes = 256;
 constexpr int kOffHead = kOffOnes + kOnesBytes;              // w_sigma[256] w_rgb[3][128] b_sigma b_rgb[3]
@@ -1027,7 +1021,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 
 size_t mlp_tc_workspace_bytes(int64_t M, int save) { return ws_layout(M, save).total; }
 
-static int sm_count_cached = 0;
 static int num_ctas() {         // NERF_TC_CTAS_RT=1|2 overrides the compiled default (kernel-variant sweeps)
   static int n = [] {
     const char* e = getenv("NERF_TC_CTAS_RT");
@@ -1038,19 +1031,17 @@ static int num_ctas() {         // NERF_TC_CTAS_RT=1|2 overrides the compiled de
 }
 template <bool kBwd, bool kSave, int kCtas, bool kSigmaOnly = false>
 static int launch_tc_impl(const TcArgs& a, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    int dev = 0;
-    NERF_CUDA(cudaGetDevice(&dev));
-    cudaDeviceProp p;
-    NERF_CUDA(cudaGetDeviceProperties(&p, dev));
-    NERF_CHECK_ARG(p.major == 10, "libnerf_b200 needs an sm_100 device (found sm_%d%d); there is no fallback", p.major, p.minor);
-    sm_count_cached = p.multiProcessorCount;
+  static DeviceOnce attr_done;                      // per kernel instantiation AND per device
+  DeviceProps dp;
+  int rc = current_device(&dp);
+  if (rc) return rc;
+  if (attr_done.needed(dp.ordinal)) {
+    NERF_CHECK_ARG(dp.sm_major == 10, "libnerf_b200 needs an sm_100 device (found sm_%d%d); there is no fallback", dp.sm_major, dp.sm_minor);
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<kBwd, kSave, kCtas, kSigmaOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_done = true;
+    attr_done.mark(dp.ordinal);
   }
   const int units = (kCtas == 2) ? (a.num_pairs + 1) / 2 : a.num_pairs;
-  const int max_units = sm_count_cached / kCtas;
+  const int max_units = dp.sm_count / kCtas;
   const int grid = (units < max_units ? units : max_units) * kCtas;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);

@@ -318,16 +318,14 @@ int mlp_tc_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t 
   add(DPRE(8), 65536, 2, ACT(7), 65536, 256, L_BOTT, 0, 256, true, 8);                     // bottleneck_linear
   add(dhv, 32768, 1, ACT(8), 65536, 256, L_VIEW, 0, 256, true, 6);                         // view_linear: bottleneck columns + bias
   add(dhv, 32768, 1, de16, 16384, 64, L_VIEW, 256, 27, false, 3);                          // view_linear: direction columns
-  static int sm_count = 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    int dev = 0;
-    NERF_CUDA(cudaGetDevice(&dev));
-    cudaDeviceProp p;
-    NERF_CUDA(cudaGetDeviceProperties(&p, dev));
-    sm_count = p.multiProcessorCount;
+  static DeviceOnce attr_done;
+  DeviceProps dp;
+  int rc = current_device(&dp);
+  if (rc) return rc;
+  const int sm_count = dp.sm_count;
+  if (attr_done.needed(dp.ordinal)) {
     NERF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
-    attr_done = true;
+    attr_done.mark(dp.ordinal);
   }
   int wsum = 0;
   for (int j = 0; j < nj; ++j) wsum += jobs[j].nslabs;
@@ -349,8 +347,7 @@ int mlp_tc_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t 
   // created once per device on the first call.
   static cudaStream_t side[16] = {};
   static cudaEvent_t ev_fork[16] = {}, ev_join[16] = {};
-  int dev = 0;
-  NERF_CUDA(cudaGetDevice(&dev));
+  const int dev = dp.ordinal;
   NERF_CHECK_ARG(dev >= 0 && dev < 16, "mlp_tc_wgrad: device ordinal %d out of range", dev);
   if (side[dev] == nullptr) {
     NERF_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));

@@ -531,11 +531,14 @@ extern "C" int nerf_composite_train(const float* raw, const float* z_vals, const
 
 static int launch_pdf(const PdfArgs& a, bool merge, cudaStream_t st) {
   const size_t smem = (size_t)kPdfWarps * (2 * kMaxBins + (merge ? kMaxSort : 0)) * sizeof(float);
-  static bool attr_set[2] = {false, false};
+  static DeviceOnce attr_set;                       // per device (function attributes are per context)
   if (merge) {
-    if (!attr_set[1]) {
+    DeviceProps dp;
+    int rc = current_device(&dp);
+    if (rc) return rc;
+    if (attr_set.needed(dp.ordinal)) {
       NERF_CUDA(cudaFuncSetAttribute(sample_pdf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set[1] = true;
+      attr_set.mark(dp.ordinal);
     }
     sample_pdf_kernel<true><<<ceil_div(a.R, kPdfWarps), kPdfWarps * 32, smem, st>>>(a);
   } else {

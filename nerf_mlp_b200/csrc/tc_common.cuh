@@ -57,8 +57,9 @@ constexpr int kMaxSlots = 192;
 // ---- bf16-mode workspace (byte offsets) -----------------------------------------------------------
 // Saved activations / gradients live in HBM as SHARED-MEMORY TILE IMAGES: per 128-row tile and
 // per 64-feature block a contiguous 16 KB block [128 rows][128 B] with the 16-byte chunks XOR-
-// swizzled by (row & 7) -- byte for byte what the kernels hold in shared memory.  A save is then
-// one TMA bulk store of the tile, and the wgrad kernel's operand loads are plain TMA bulk loads.
+// swizzled by (row & 7) -- byte for byte what the kernels hold in shared memory.  A save is then a
+// per-warp coalesced 4 KB block copy (LDS.128 -> STG.128), and the wgrad kernel's operand loads are plain
+// bulk-async copies (cp.async.bulk, SASS UBLKCP -- contiguous blocks, no tensor map needed).
 //   element (row r, feature f) of a tensor with F features (F/64 blocks per tile):
 //     tile = r / 128, rt = r % 128, fb = f / 64
 //     byte = tile * (F/64) * 16384 + fb * 16384 + rt * 128 + ((((f % 64) / 8) ^ (rt & 7)) * 16) + (f % 8) * 2
@@ -69,8 +70,8 @@ constexpr int kMaxSlots = 192;
 //           xenc  img  [Mp x 64]     encoded position (63 used)                           (save only)
 //           de16  img  [Mp x 64]     encoded view direction per sample (27 used)          (save only)
 //           mask  u32  [8][M][8]     ReLU masks of h0..h7; hvmask u32 [M][4]   (row-major, save only)
-// backward: dpre  img  [9][Mp x 256] d(pre-activation) of layers 0..7, d(bottleneck); dhv img [Mp x 128];
-//           draw16 img [Mp x 64]     d_raw as bf16 (4 used)   -- Mp = rows padded to a multiple of 512
+// backward: dpre  img  [9][Mp x 256] d(pre-activation) of layers 0..7, d(bottleneck); dhv img [Mp x 128]
+//           -- Mp = rows padded to a multiple of 512 (whole tile quads per CTA pair)
 struct WsLayout {
   size_t vb, de, act, hv, xenc, de16, mask, hvmask, dpre, dhv, total;
   int64_t Mp;

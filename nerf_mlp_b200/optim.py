@@ -14,7 +14,11 @@ class FlatAdam(torch.optim.Optimizer):
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None, world_size=None):
         self.model = model
-        super().__init__(model._param_list, dict(lr=lr, betas=betas, eps=eps))
+        # the full set of torch.optim.Adam defaults: a state_dict written by a FRESH FlatAdam must load into the
+        # reference's torch.optim.Adam (which replaces its param_groups wholesale and then reads group['weight_decay'] etc.)
+        super().__init__(model._param_list, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False,
+                                                 foreach=None, capturable=False, differentiable=False, fused=None,
+                                                 decoupled_weight_decay=False))
         self._step = 0
         self._m = None
         self._v = None
@@ -28,6 +32,13 @@ class FlatAdam(torch.optim.Optimizer):
             return torch.distributed.get_world_size(self.process_group)
         return 1
 
+    def _ensure_moments(self):
+        """(Re-)create zero Adam moments on the model's device (fresh optimizer, or a checkpoint saved before step 1)."""
+        flat = self.model.flat_params
+        if self._m is None or self._v is None or self._m.device != flat.device:
+            self._m = torch.zeros_like(flat)
+            self._v = torch.zeros_like(flat)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
@@ -40,9 +51,7 @@ class FlatAdam(torch.optim.Optimizer):
         world = self._world_size()
         if world > 1:
             torch.distributed.all_reduce(flat_g, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
-        if self._m is None or self._m.device != model.flat_params.device:
-            self._m = torch.zeros_like(model.flat_params)
-            self._v = torch.zeros_like(model.flat_params)
+        self._ensure_moments()
         self._step += 1
         g = self.param_groups[0]
         ops.adam_step(model.flat_params, flat_g, self._m, self._v, self._step, g["lr"], g["betas"], g["eps"],
@@ -53,7 +62,8 @@ class FlatAdam(torch.optim.Optimizer):
     # ---- checkpoint interop: the reference saves torch.optim.Adam's state_dict ------------------
     # (scripts/train.py:471-475 'optimizer_state_dict') and resumes from it (:303-306).  FlatAdam
     # writes and reads exactly that format -- per-parameter {'step','exp_avg','exp_avg_sq'} in
-    # state_dict order -- so checkpoints move between the reference and this package both ways.
+    # state_dict order, param_groups with every torch.optim.Adam key -- so checkpoints move between the
+    # reference and this package both ways (tests/test_host_cpu.py: fresh FlatAdam -> torch Adam -> step).
     def state_dict(self):
         sd = super().state_dict()
         state = {}

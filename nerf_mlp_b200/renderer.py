@@ -26,7 +26,7 @@ class NeRFRenderer:
                  pos_enc_L=10, dir_enc_L=4,
                  N_samples=64, N_importance=128,
                  near=2.0, far=6.0, white_bkgd=True, perturb=1.0, raw_noise_std=0.0, coord_scale=1.0,
-                 *, precision=None, coarse_grad=False, coarse_density_only=True):
+                 *, precision=None, coarse_grad=None, coarse_density_only=True):
         if not isinstance(model, NeRFMLP):
             raise TypeError("nerf_mlp_b200.NeRFRenderer needs a nerf_mlp_b200.NeRFMLP (the fused kernels "
                             "own the network; there is no generic nn.Module path)")
@@ -46,7 +46,11 @@ class NeRFRenderer:
         self.dir_enc = PositionalEncoding(dir_enc_L).to(device)
         # extras (keyword-only, defaults keep the reference's behaviour)
         self.precision = precision            # None -> follow model.precision
-        self.coarse_grad = coarse_grad        # reference training never back-props the coarse maps
+        # None (default) = the reference's behaviour: under autograd the coarse maps are differentiable, so a caller
+        # who adds the usual coarse MSE term gets its gradient (renderer.py:79-80 builds them with grad).  False is the
+        # explicit opt-out (coarse pass under no_grad: faster, *_coarse maps come back detached); True additionally
+        # makes TrainStep refuse, because its fused step implements the reference's fine-only loss.
+        self.coarse_grad = coarse_grad
         # render() / TrainStep: evaluate the coarse pass for its densities only (its colour maps are dropped by
         # render(), renderer.py:44, and unused by the loss); False = the whole network in both passes
         self.coarse_density_only = coarse_density_only
@@ -124,7 +128,7 @@ class NeRFRenderer:
         fine = self.N_importance > 0
         density_only = bool(_coarse_density_only) and fine and not grad
         rgb0, depth0, acc0, weights = self._pass(rays_o, rays_d, z_vals,
-                                                 grad and (self.coarse_grad or not fine), density_only)  # :63-80
+                                                 grad and (self.coarse_grad is not False or not fine), density_only)  # :63-80
         if not fine:
             return {'rgb_map': rgb0, 'depth_map': depth0, 'acc_map': acc0}                       # :112
 

@@ -56,17 +56,16 @@ class TrainStep:
             raise ValueError("TrainStep: optimizer and renderer must share one NeRFMLP")
         if renderer.N_importance <= 0:
             raise NotImplementedError("TrainStep implements the coarse+fine step (N_importance > 0)")
-        if renderer.coarse_grad:
+        if renderer.coarse_grad is True:
             raise NotImplementedError("TrainStep implements the reference's loss (fine rgb_map only, "
-                                      "scripts/train.py:374-376); coarse_grad=True needs the autograd path")
+                                      "scripts/train.py:374-376), whose coarse-pass gradient is identically zero; "
+                                      "an explicit coarse_grad=True (a coarse loss term) needs the autograd path")
         self.R = int(n_rays)
         self.dev = renderer.device
         m = self.model
         m._ensure_flat()
         m._bind_flat_grads()
-        if optimizer._m is None or optimizer._m.device != m.flat_params.device:
-            optimizer._m = torch.zeros_like(m.flat_params)
-            optimizer._v = torch.zeros_like(m.flat_params)
+        optimizer._ensure_moments()
         f32 = dict(device=self.dev, dtype=torch.float32)
         self._inputs = torch.zeros((3, self.R, 3), **f32)     # static batch buffers of the captured step (one block)
         self.rays_o, self.rays_d, self.target = self._inputs[0], self._inputs[1], self._inputs[2]
@@ -205,6 +204,7 @@ class TrainStep:
         m, opt = self.model, self.opt
         m._ensure_flat()
         m._bind_flat_grads()
+        opt._ensure_moments()                                   # a checkpoint saved before the first step loads as None
         return (m.flat_params.data_ptr(), m._flat_grad.data_ptr(), opt._m.data_ptr(), opt._v.data_ptr(),
                 m._packed.data_ptr() if m._packed is not None else 0)
 
@@ -215,6 +215,7 @@ class TrainStep:
         m, opt = self.model, self.opt
         if r_is_bf16(self.renderer):
             m.packed_weights()                                        # clean packed image before capture
+        opt._ensure_moments()
         snap = (m.flat_params.clone(), opt._m.clone(), opt._v.clone(), self.state.clone())
         rng = torch.cuda.get_rng_state(self.dev)
         s = torch.cuda.Stream(self.dev)

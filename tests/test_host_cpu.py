@@ -235,6 +235,29 @@ def test_optimizer_state_interchanges_with_torch_adam(tmp_path):
         opt.load_state_dict(bad)
 
 
+def test_fresh_flat_adam_state_loads_into_torch_adam():
+    """A FlatAdam that never loaded a torch checkpoint writes param_groups with EVERY torch.optim.Adam key, so the
+    reference's optimizer (scripts/train.py:303-306: optimizer.load_state_dict) can resume from it and step --
+    both before the first step (empty state) and after some steps (moments carried over)."""
+    ref_keys = set(torch.optim.Adam(torch.nn.Linear(2, 2).parameters()).state_dict()["param_groups"][0])
+    torch.manual_seed(3)
+    m = nb.NeRFMLP()
+    opt = nb.FlatAdam(m, lr=5e-4)
+    sd0 = opt.state_dict()
+    assert set(sd0["param_groups"][0]) == ref_keys and sd0["state"] == {}
+    m_t = nb.NeRFMLP()
+    m_t.load_state_dict(m.state_dict())
+    opt_t = torch.optim.Adam(m_t.parameters(), lr=1.0)
+    opt_t.load_state_dict(sd0)                          # raised KeyError('weight_decay') on step() before the fix
+    _adam_steps(opt_t, m_t, 5, 1)
+    assert opt_t.param_groups[0]["lr"] == 5e-4
+    # an empty-state checkpoint loaded back into FlatAdam leaves it steppable (moments re-created lazily)
+    opt.load_state_dict(sd0)
+    assert opt._step == 0 and opt._m is None
+    opt._ensure_moments()
+    assert opt._m is not None and float(opt._m.abs().sum()) == 0.0
+
+
 def test_weight_files(tmp_path):
     """.pth state_dict and the official .npy weight list (render_example.py:166-208, model.py:83-127)."""
     p = O.init_params(4)
@@ -273,9 +296,21 @@ def test_bench_reference_arm_prints_one_json_line():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["metric"] == "train_rays_per_s" and d["unit"] == "rays/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
-    assert "torch CPU restatement" in d["cpu_baseline"]["sample"] and d["config"]["rays_per_gpu"] == 128
+    # oracle/_ref (the unmodified reference, compiled by oracle/build_ref.py) when it is built, else the bit-identical port
+    from oracle import build_ref
+    kind = "reference" if build_ref.available()[0] else "port"
+    assert d["cpu_baseline"]["kind"] == kind and d["cpu_baseline"]["cores"] >= 1
+    assert ("unmodified reference" if kind == "reference" else "torch CPU restatement") in d["cpu_baseline"]["sample"]
+    assert d["config"]["rays_per_gpu"] == 128 and d["steps"] == 1 and d["warmup"] == 0      # --steps / --warmup are honoured
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    # the forced port arm still works (what a box without oracle/_ref runs)
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--rays", "64",
+                          "--cpu-port", "torch"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    d2 = json.loads(res.stdout.strip())
+    assert d2["cpu_baseline"]["kind"] == "port" and "torch CPU restatement" in d2["cpu_baseline"]["sample"]
+    assert {k: v for k, v in d2["config"].items() if k not in ("workload", "rays_per_gpu")} == \
+           {k: v for k, v in d["config"].items() if k not in ("workload", "rays_per_gpu")}
 
 
 def test_oracle_is_only_reachable_from_checker_and_baseline_code():
@@ -291,7 +326,7 @@ def test_oracle_is_only_reachable_from_checker_and_baseline_code():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f.endswith((".cu", ".cuh")) and "import" not in txt, os.path.join(dirpath, f)
     tree = ast.parse(open(os.path.join(root, "bench.py")).read())
-    allowed = {"cpu_step_fn", "time_torch_eager_gpu"}
+    allowed = {"cpu_step_fn", "cpu_kind", "time_torch_eager_gpu"}
     for node in tree.body:
         if isinstance(node, (ast.Import, ast.ImportFrom)):
             mod = getattr(node, "module", None) or ""
