@@ -95,6 +95,7 @@ def parse():
     ap.add_argument("--no-render", action="store_true", help="train workload: skip the `render` record (configs[2])")
     ap.add_argument("--with-4096", action="store_true", help="train workload: add the `train_4096` record (configs[3]) at N=1 too")
     ap.add_argument("--render-steps", type=int, default=3, help="timed steps of the `render` record")
+    ap.add_argument("--dp-parity-only", action="store_true", help="N > 1: run only the `dp_parity` numerical check and print it")
     args = ap.parse_args()
     args.steps_given, args.warmup_given = args.steps is not None, args.warmup is not None
     if args.steps is None:
@@ -859,6 +860,14 @@ def main():
         torch.cuda.synchronize()
     cx.barrier = barrier
     K, W = args.steps, max(args.warmup, 3)
+    if args.dp_parity_only:
+        if world < 2:
+            raise SystemExit("--dp-parity-only needs N > 1 ranks (torchrun)")
+        rec = dp_parity(cx, args)
+        if rank == 0:
+            emit({"dp_parity": rec})
+        td.destroy_process_group()
+        return
 
     common = {"n_gpus": world, "higher_is_better": True, "vs_baseline": None, "dtype": args.precision, "data": "synthetic"}
     if args.workload == "train":

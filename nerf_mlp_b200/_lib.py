@@ -56,6 +56,11 @@ SIGNATURES = {
 _dll = None
 
 
+def bwd_fused():
+    """True unless NERF_BWD_FUSED=0 selects the two-kernel backward (the library reads the same variable)."""
+    return os.environ.get("NERF_BWD_FUSED", "1")[:1] != "0"
+
+
 def dll():
     """Load the shared library once.  Fails loudly when it has not been built."""
     global _dll

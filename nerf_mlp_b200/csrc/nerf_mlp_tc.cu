@@ -1099,6 +1099,16 @@ int mlp_tc_forward(const float* rays_o, const float* rays_d, const float* z_vals
   return save ? launch_tc<false, true>(a, st) : launch_tc<false, false>(a, st);
 }
 
+}  // namespace nerf
+#include "nerf_mlp_bwd_fused.cuh"
+namespace nerf {
+
+// NERF_BWD_FUSED=0 selects the two-kernel backward (dgrad chain, then wgrad) for A/B measurements
+static bool bwd_fused_enabled() {
+  static const bool on = [] { const char* e = getenv("NERF_BWD_FUSED"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 int mlp_tc_backward(const float* d_raw, int64_t M, int rows_per_dir, const float* params, const void* packed,
                     float* grads, void* ws, size_t ws_bytes, int stage, cudaStream_t st) {
   const WsLayout L = ws_layout(M, 1);
@@ -1111,8 +1121,14 @@ int mlp_tc_backward(const float* d_raw, int64_t M, int rows_per_dir, const float
   a.d_raw = d_raw; a.M = M; a.packed = (const uint8_t*)packed; a.params = params;
   fill_saved(a, ws, L);
   a.num_pairs = (int)(L.Mp / (2 * kTileM));   // the whole padded tile range: every tile image the wgrad kernel reads is written (single-CTA mode too)
+  if (stage == NERF_BWD_ALL && bwd_fused_enabled()) {
+    // one launch: dgrad chain + tensor-core weight gradients; the two tiny heads (rgb, sigma) follow on CUDA cores
+    if ((rc = launch_bwd_fused(a, ws, L, grads, st))) return rc;
+    return mlp_tc_heads_wgrad(ws, L, d_raw, M, grads, st);
+  }
   if (stage != NERF_BWD_WGRAD && (rc = launch_tc<true, false>(a, st))) return rc;     // d(pre-activations) -> workspace
   if (stage == NERF_BWD_DGRAD) return 0;
+
   return mlp_tc_wgrad(ws, L, d_raw, M, rows_per_dir, grads, st);            // weight / bias gradients
 }
 

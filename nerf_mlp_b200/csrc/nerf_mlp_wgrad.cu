@@ -288,6 +288,16 @@ __global__ void __launch_bounds__(32 * kHeadsWarps) heads_wgrad_kernel(const flo
   }
 }
 
+// rgb / sigma head gradients alone (the fused backward kernel does everything else)
+int mlp_tc_heads_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t M, float* grads, cudaStream_t st) {
+  const uint8_t* b = (const uint8_t*)ws;
+  const int64_t ntiles = L.Mp / kTileM;
+  heads_wgrad_kernel<<<ceil_div(M, (int64_t)kHeadsWarps * kHeadsRowsPerWarp), 32 * kHeadsWarps, 0, st>>>(
+      d_raw, b + L.hv, b + L.act + (int64_t)7 * ntiles * 65536, M, grads);
+  NERF_LAUNCH_CHECK("heads_wgrad_kernel");
+  return 0;
+}
+
 int mlp_tc_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t M, int rows_per_dir, float* grads,
                  cudaStream_t st) {
   (void)rows_per_dir;   // the per-sample direction encodings were saved by the forward (de16)

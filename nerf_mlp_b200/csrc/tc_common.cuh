@@ -71,9 +71,10 @@ constexpr int kMaxSlots = 192;
 //           de16  img  [Mp x 64]     encoded view direction per sample (27 used)          (save only)
 //           mask  u32  [8][M][8]     ReLU masks of h0..h7; hvmask u32 [M][4]   (row-major, save only)
 // backward: dpre  img  [9][Mp x 256] d(pre-activation) of layers 0..7, d(bottleneck); dhv img [Mp x 128]
+//           flags u32  [10][Mp/128]   fused backward: number of warps that have published (d_pre_0..7, d_bott, d_hv) of a tile
 //           -- Mp = rows padded to a multiple of 512 (whole tile quads per CTA pair)
 struct WsLayout {
-  size_t vb, de, act, hv, xenc, de16, mask, hvmask, dpre, dhv, total;
+  size_t vb, de, act, hv, xenc, de16, mask, hvmask, dpre, dhv, flags, total;
   int64_t Mp;
 };
 inline WsLayout ws_layout(int64_t M, int save) {
@@ -92,6 +93,7 @@ inline WsLayout ws_layout(int64_t M, int save) {
     w.hvmask = take((size_t)M * 4 * 4);
     w.dpre = take((size_t)9 * w.Mp * 256 * 2);
     w.dhv = take((size_t)w.Mp * 128 * 2);
+    w.flags = take(((size_t)10 * (w.Mp / kTileM) + 32) * 4);   // fused backward: publish counters [10 tensors][tiles] + unit counter
   }
   w.total = o;
   return w;
@@ -99,5 +101,6 @@ inline WsLayout ws_layout(int64_t M, int save) {
 
 int mlp_tc_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t M, int rows_per_dir, float* grads,
                  cudaStream_t st);
+int mlp_tc_heads_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t M, float* grads, cudaStream_t st);
 
 }  // namespace nerf

@@ -200,7 +200,8 @@ def bf16_workspace_views(ws, M):
             ("mask", 8 * M * 8 * 4, torch.int32, (8, M, 8), None),
             ("hvmask", M * 4 * 4, torch.int32, (M, 4), None),
             ("dpre", 9 * Mp * 256 * 2, torch.bfloat16, None, (9, 256)),
-            ("dhv", Mp * 128 * 2, torch.bfloat16, None, (1, 128)))
+            ("dhv", Mp * 128 * 2, torch.bfloat16, None, (1, 128)),
+            ("flags", (10 * (Mp // 128) + 32) * 4, torch.int32, (10 * (Mp // 128) + 32,), None))
     for name, nbytes, dt, shape, img in spec:
         flat = ws[off:off + nbytes].view(dt)
         if img is None:
@@ -239,12 +240,18 @@ class RenderPassFn(torch.autograd.Function):
     def forward(ctx, model, rays_o, rays_d, z_vals, noise, white_bkgd, coord_scale, precision, save, *params):
         # `save` is decided by the caller: grad mode is always off inside Function.forward
         # save == "density": weights-only coarse pass (rgb/depth/acc maps of this pass are not meaningful)
+        # save == "lazy":    differentiable WITHOUT paying for it up front: the forward runs the inference kernel (nothing
+        #                    saved); if a gradient ever reaches this pass, backward() re-runs the forward in save mode on
+        #                    the same samples / noise first (activation checkpointing of the whole pass).  Used for the
+        #                    coarse pass, whose maps the reference returns differentiable but never puts in its loss.
         density = isinstance(save, str) and save == "density"
-        raw, ws = mlp_fwd_rays(model, rays_o, rays_d, z_vals, coord_scale, precision, False if density else save,
+        lazy = isinstance(save, str) and save == "lazy"
+        raw, ws = mlp_fwd_rays(model, rays_o, rays_d, z_vals, coord_scale, precision, False if (density or lazy) else save,
                                density_only=density)
         rgb, depth, acc, w = composite_fwd(raw, z_vals, rays_d, noise, white_bkgd, True)
         ctx.model, ctx.white, ctx.precision = model, white_bkgd, precision
         ctx.ws, ctx.noise = ws, noise
+        ctx.lazy = (rays_o, float(coord_scale)) if lazy else None
         ctx.save_for_backward(raw, z_vals, rays_d)
         ctx.mark_non_differentiable(w)
         return rgb, depth, acc, w
@@ -252,6 +259,9 @@ class RenderPassFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_rgb, d_depth, d_acc, _d_w):
         raw, z, d = ctx.saved_tensors
+        if ctx.ws is None and ctx.lazy is not None:
+            rays_o, coord_scale = ctx.lazy                    # recompute the pass in save mode (same z, same noise)
+            raw, ctx.ws = mlp_fwd_rays(ctx.model, rays_o, d, z, coord_scale, ctx.precision, True)
         if ctx.ws is None:
             raise RuntimeError("RenderPassFn.backward: forward ran without saving activations")
         d_rgb = _cg(d_rgb) if d_rgb is not None else torch.zeros_like(d)

@@ -46,10 +46,11 @@ class NeRFRenderer:
         self.dir_enc = PositionalEncoding(dir_enc_L).to(device)
         # extras (keyword-only, defaults keep the reference's behaviour)
         self.precision = precision            # None -> follow model.precision
-        # None (default) = the reference's behaviour: under autograd the coarse maps are differentiable, so a caller
-        # who adds the usual coarse MSE term gets its gradient (renderer.py:79-80 builds them with grad).  False is the
-        # explicit opt-out (coarse pass under no_grad: faster, *_coarse maps come back detached); True additionally
-        # makes TrainStep refuse, because its fused step implements the reference's fine-only loss.
+        # None (default) = the reference's behaviour at no cost: under autograd the coarse maps ARE differentiable
+        # (renderer.py:79-80 builds them with grad, so a caller who adds the usual coarse MSE term gets its gradient),
+        # but lazily -- the coarse forward runs the inference kernel and is re-run in save mode only if a gradient
+        # actually reaches it (ops.RenderPassFn save="lazy").  True saves eagerly (and makes TrainStep refuse: its fused
+        # step implements the reference's fine-only loss).  False is the explicit opt-out (*_coarse come back detached).
         self.coarse_grad = coarse_grad
         # render() / TrainStep: evaluate the coarse pass for its densities only (its colour maps are dropped by
         # render(), renderer.py:44, and unused by the loss); False = the whole network in both passes
@@ -70,13 +71,14 @@ class NeRFRenderer:
         return t
 
     def _pass(self, rays_o, rays_d, z_vals, want_grad, density_only=False):
+        """want_grad: False | True (save activations now) | "lazy" (differentiable, recomputed on demand)."""
         noise = None
         if self.raw_noise_std > 0.:
             noise = (torch.randn(z_vals.shape, device=z_vals.device) * self.raw_noise_std).contiguous()  # :134-136
         m = self.model
         if want_grad:
             return ops.RenderPassFn.apply(m, rays_o, rays_d, z_vals, noise, bool(self.white_bkgd),
-                                          float(self.coord_scale), self._prec(), True, *m._param_list)
+                                          float(self.coord_scale), self._prec(), want_grad, *m._param_list)
         with torch.no_grad():
             return ops.RenderPassFn.apply(m, rays_o, rays_d, z_vals, noise, bool(self.white_bkgd),
                                           float(self.coord_scale), self._prec(), "density" if density_only else False,
@@ -127,8 +129,13 @@ class NeRFRenderer:
         z_vals = ops.stratified_z(self._linspace(self.N_samples), t_rand, N_rays, self.near, self.far)
         fine = self.N_importance > 0
         density_only = bool(_coarse_density_only) and fine and not grad
-        rgb0, depth0, acc0, weights = self._pass(rays_o, rays_d, z_vals,
-                                                 grad and (self.coarse_grad is not False or not fine), density_only)  # :63-80
+        if not grad or (fine and self.coarse_grad is False):
+            coarse_mode = False
+        elif fine and self.coarse_grad is None:
+            coarse_mode = "lazy"
+        else:
+            coarse_mode = True
+        rgb0, depth0, acc0, weights = self._pass(rays_o, rays_d, z_vals, coarse_mode, density_only)  # :63-80
         if not fine:
             return {'rgb_map': rgb0, 'depth_map': depth0, 'acc_map': acc0}                       # :112
 

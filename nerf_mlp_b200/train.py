@@ -48,7 +48,8 @@ class TrainStep:
     (one D2H copy + sync, for the periodic logging the reference does every step).
     """
 
-    def __init__(self, renderer, optimizer, n_rays, *, graph=True, warmup=2, stage_events=False, split_graphs=None):
+    def __init__(self, renderer, optimizer, n_rays, *, graph=True, warmup=2, stage_events=False, split_graphs=None,
+                 graph_allreduce=True):
         self.renderer, self.opt, self.model = renderer, optimizer, renderer.model
         if torch.device(renderer.device).type != "cuda":
             raise RuntimeError("nerf_mlp_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -88,6 +89,11 @@ class TrainStep:
         # two graphs (forward+backward | metrics+Adam+repack) with the eager all-reduce between them: always
         # at world_size > 1; split_graphs=True forces the same structure on one GPU (tests)
         self.split_graphs = split_graphs
+        # world_size > 1: capture the NCCL all-reduce INSIDE the one step graph (no host round trip between two
+        # replays: the exchange costs its device time only).  Falls back to two graphs with an eager all-reduce in
+        # between if the capture is refused by the installed NCCL / PyTorch.
+        self.graph_allreduce = bool(graph_allreduce)
+        self.allreduce_in_graph = False
         self._marks = []
         self._push_state(force=True)
         if self.use_graph:
@@ -161,13 +167,14 @@ class TrainStep:
                                          ptr(self._scratch_c), ptr(m._flat_grad), m._flat_grad.numel(),
                                          stream_ptr(self.dev)), "nerf_composite_train")
         self._mark("composite_train(fwd+mse+bwd+zero_grad)")
-        if self.stage_events:                                                # same launches, one mark in between
+        if self.stage_events and not (_lib.bwd_fused() and prec == _lib.PREC_BF16):   # two-kernel backward: one mark in between
             ops.mlp_bwd(m, d_raw, ws, prec, m._flat_grad, z_fine.shape[1], _lib.BWD_DGRAD)
             self._mark("mlp_bwd_dgrad")
             ops.mlp_bwd(m, d_raw, ws, prec, m._flat_grad, z_fine.shape[1], _lib.BWD_WGRAD)
             self._mark("mlp_bwd_wgrad")
         else:
-            ops.mlp_bwd(m, d_raw, ws, prec, m._flat_grad, z_fine.shape[1])
+            ops.mlp_bwd(m, d_raw, ws, prec, m._flat_grad, z_fine.shape[1])       # fused dgrad + wgrad launch (+ heads)
+            self._mark("mlp_bwd")
         self.outputs = {"rgb_map": rgb, "depth_map": depth, "acc_map": acc}
         if not dens:
             self.outputs.update({"rgb_map_coarse": rgb0, "depth_map_coarse": depth0, "acc_map_coarse": acc0})
@@ -229,15 +236,30 @@ class TrainStep:
         pool = None
         launches0 = dll().nerf_launch_count()
         with torch.no_grad():
-            split = self._world() > 1 if self.split_graphs is None else (self.split_graphs or self._world() > 1)
-            parts = [(self._fwd_bwd,), (self._update,)] if split else [(self._fwd_bwd, self._update)]
-            for fns in parts:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
-                    for fn in fns:
-                        self._keep.append(fn())
-                pool = g.pool()
-                self._graphs.append(g)
+            multi = self._world() > 1
+            split = multi if self.split_graphs is None else (self.split_graphs or multi)
+            self.allreduce_in_graph = False
+            if multi and self.graph_allreduce and not self.split_graphs:
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._keep.append(self._fwd_bwd())
+                        self._allreduce()
+                        self._keep.append(self._update())
+                    self._graphs.append(g)
+                    self.allreduce_in_graph = True
+                except Exception:                                     # capture of the collective refused: two graphs
+                    torch.cuda.synchronize(self.dev)
+                    self._graphs, self._keep, self._marks = [], [], []
+            if not self._graphs:
+                parts = [(self._fwd_bwd,), (self._update,)] if split else [(self._fwd_bwd, self._update)]
+                for fns in parts:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool):
+                        for fn in fns:
+                            self._keep.append(fn())
+                    pool = g.pool()
+                    self._graphs.append(g)
         launches_after = dll().nerf_launch_count()
         torch.cuda.synchronize(self.dev)
         with torch.no_grad():

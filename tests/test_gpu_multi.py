@@ -1,0 +1,38 @@
+"""Numerical checks on REAL ranks (needs >= 2 GPUs on the box: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`;
+skipped on the driver's 1-GPU pytest box -- the same check runs inside every multi-GPU `bench.py` line as `dp_parity`).
+
+  * k data-parallel TrainStep steps (one NCCL all-reduce of the flat gradient per step, scripts/train.py:376 global-mean
+    semantics) leave bit-identical parameters on every rank and match k single-rank steps on the
+    concatenated batch;
+  * dist.render_sharded over the ranks == NeRFRenderer.render on one rank, bit for bit.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("world", [2])
+def test_dp_training_and_sharded_render_match_single_rank(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (found {torch.cuda.device_count()}); covered by bench.py's dp_parity record at N > 1")
+    env = dict(os.environ)
+    env.pop("OMP_NUM_THREADS", None)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "bench.py"),
+                          "--gpus", str(world), "--dp-parity-only"], capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stderr[-3000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
+    rec = json.loads(line)["dp_parity"]
+    print(rec)
+    assert rec["world"] == world
+    assert rec["params_differ_across_ranks"] == 0
+    assert rec["sharded_render_mismatching_values"] == 0
+    assert rec["dp_vs_single_rel_l2_of_update"] <= 2e-2 and rec["loss_rel_diff_max"] <= 1e-4
+    assert rec["ok"]

@@ -203,23 +203,25 @@ def test_data_parallel_graph_structure(nb):
     R = 96
     o, d, tgt = batch(R, 41)
     out = {}
-    for kind in ("single", "split", "world2"):
+    for kind in ("single", "split", "world2", "world2_one_graph"):
         m, r, opt = make(nb, 11, "bf16", 0.0)
         cls = nb.TrainStep
-        if kind == "world2":
+        if kind.startswith("world2"):
             opt._world = 2
 
             class TwoIdenticalRanks(nb.TrainStep):
                 def _allreduce(self):                               # sum over two ranks holding the same batch
                     self.model._flat_grad.mul_(2.0)
             cls = TwoIdenticalRanks
-        step = cls(r, opt, R, split_graphs=(kind != "single"))
-        if kind == "world2":
+        # world2_one_graph: the default at world_size > 1 -- the exchange is captured inside the single step graph
+        step = cls(r, opt, R, split_graphs=(None if kind == "world2_one_graph" else kind != "single"))
+        if kind.startswith("world2"):
             assert float(step.state[4]) == 0.5
         losses = [float(step(o, d, tgt)) for _ in range(3)]
-        assert len(step._graphs) == (1 if kind == "single" else 2)
+        assert len(step._graphs) == (1 if kind in ("single", "world2_one_graph") else 2)
+        assert step.allreduce_in_graph == (kind == "world2_one_graph")
         out[kind] = (losses, m.flat_params.detach().cpu().numpy().copy(), step.read_metrics()["grad_norm"])
-    for kind in ("split", "world2"):
+    for kind in ("split", "world2", "world2_one_graph"):
         assert out[kind][0][0] == out["single"][0][0]
         np.testing.assert_allclose(out[kind][0], out["single"][0], rtol=2e-4)
         np.testing.assert_allclose(out[kind][1], out["single"][1], atol=2.1e-3)
