@@ -41,6 +41,17 @@ using namespace ptx;
 // Measured and dropped: dedicated store warps and TMA bulk stores for the tile-image saves (both
 // slower than the per-warp coalesced copies: bulk S2G 0.34 vs 0.31 ms on the 196 608-row save pass).
 constexpr int kThreads = 352;                     // producer, 2 mma issuers, 8 prologue/epilogue warps
+// Kernels that write tile images to HBM (save-mode forward, dgrad chain) get 4 more warps that do nothing but the
+// copy-out: the tile in shared memory is byte for byte its HBM image, so a copy warp moves one whole 16 KB feature
+// block with coalesced LDS.128 / STG.128 while the eight compute warps -- which then share every epilogue exactly as in
+// the inference kernel -- are already waiting for the next accumulator.  (Round 1 had the epilogue warps copy their
+// own blocks out: ~2 000 clk per tile-layer on the dependent chain MMA -> epilogue -> MMA.)
+#ifndef NERF_TC_COPY_WARPS
+#define NERF_TC_COPY_WARPS 4
+#endif
+constexpr int kCopyWarps = NERF_TC_COPY_WARPS;
+constexpr int kThreadsStore = kThreads + 32 * kCopyWarps;
+template <bool kStores> constexpr int tc_threads() { return (kStores && kCopyWarps > 0) ? kThreadsStore : kThreads; }
 #ifndef NERF_TC_ARRIVE_LANES
 #define NERF_TC_ARRIVE_LANES 1                    // 1 = every thread arrives on "activations ready" (default); 32 = one arrive per warp (measured: no gain, 78.7 vs 79.4 % of peak)
 #endif
@@ -95,7 +106,8 @@ constexpr int kOnesBytes = 256;
 constexpr int kOffHead = kOffOnes + kOnesBytes;              // w_sigma[256] w_rgb[3][128] b_sigma b_rgb[3]
 constexpr int kHeadFloats = 256 + 384 + 4;
 constexpr int kOffBar = kOffHead + kHeadFloats * 4;
-constexpr int kNumBars = 3 * (2 * kRing) + 5;      // sized for the 2-CTA variant (ring twice as deep)
+constexpr int kBarSets = (NERF_TC_RELAY_FULL != 0) ? 2 : 3;   // full, empty (+ the peer-landed barriers when the relay does not use `full`)
+constexpr int kNumBars = kBarSets * (2 * kRing) + 5 + 4;     // sized for the 2-CTA variant (ring twice as deep); + copy-out handshake
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 8;
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
@@ -401,10 +413,11 @@ __device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&r)[32]) {
 // (renderer.py:79-87 uses `weights`; the coarse colour maps are dropped by render(), renderer.py:44,
 // and never reach the loss, scripts/train.py:374-376).  Output rows are (0, 0, 0, sigma).
 template <bool kBwd, bool kSave, int kCtas, bool kSigmaOnly = false>
-__global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__((tc_threads<kBwd || kSave>()), 1) mlp_tc_kernel(const TcArgs a) {
   static_assert(!kSigmaOnly || (!kBwd && !kSave), "density-only mode is an inference-forward mode");
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr bool kShared = (!kBwd && !kSave) || (NERF_TC_SHARED_TRAIN != 0);   // all eight compute warps share every epilogue
+  constexpr bool kCopy = (kBwd || kSave) && kCopyWarps > 0;                     // dedicated copy-out warps (11 .. 11 + kCopyWarps - 1)
+  constexpr bool kShared = (!kBwd && !kSave) || kCopy || (NERF_TC_SHARED_TRAIN != 0);   // all eight compute warps share every epilogue
   constexpr bool kSplit = (!kBwd && !kSave) ? (NERF_TC_SPLIT_INFER != 0) : (NERF_TC_SPLIT_TRAIN != 0);   // private weight stream per tile
   constexpr int kRingK = kRing * kCtas;                 // ring slots per CTA (same bytes, half-size slots in pair mode)
   constexpr int kRingT = kSplit ? kRingK / 2 : kRingK;  // slots of one stream
@@ -421,10 +434,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (kRingK + s); };
   auto bar_pfull = [&](int s) { return bar0 + 8u * (2 * kRingK + s); };    // pair mode, leader: the peer's half of slot s landed
-  constexpr int kB0 = 3 * kRingK;
+  constexpr int kB0 = kBarSets * kRingK;
   auto bar_act = [&](int t) { return bar0 + 8u * (kB0 + t); };             // activations of tile t ready (epilogue -> MMA)
   auto bar_acc = [&](int t) { return bar0 + 8u * (kB0 + 2 + t); };         // accumulator of tile t ready (MMA -> epilogue)
   const uint32_t bar_skew = bar0 + 8u * (kB0 + 4);                         // one-shot: tile A's issuer is kSkew slots in
+  auto bar_cp = [&](int t) { return bar0 + 8u * (kB0 + 5 + t); };          // tile t complete in shared memory: copy it out (compute -> copy warps)
+  auto bar_cpfree = [&](int t) { return bar0 + 8u * (kB0 + 7 + t); };      // the copy warps have read tile t: it may be overwritten
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* head = reinterpret_cast<float*>(smem + kOffHead);
   constexpr int kNumGemms = kBwd ? kNumGemmsBwd : (kSigmaOnly ? 8 : kNumGemmsFwd);
@@ -434,10 +449,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
     for (int s = 0; s < kRingK; ++s) {
       mbar_init(bar_full(s), (kCtas == 2 && kRelayFull && rank == 0) ? 2 : 1);      // leader: own bytes + the peer's relay
       mbar_init(bar_empty(s), kSplit ? 1 : 2);
-      mbar_init(bar_pfull(s), 1);
+      if (kBarSets == 3) mbar_init(bar_pfull(s), 1);
     }
     for (int t = 0; t < 2; ++t) { mbar_init(bar_act(t), (kShared ? 256 : 128) / kArriveLanes * kCtas); mbar_init(bar_acc(t), 1); }
     mbar_init(bar_skew, 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_cp(t), 8); mbar_init(bar_cpfree(t), kCopyWarps > 0 ? kCopyWarps : 1); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -590,6 +606,48 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
         }
       }
     }
+  } else if (warp >= kFirstComputeWarp + 8) {
+    // ================= copy-out warps (save-mode forward / dgrad only) =================
+    if constexpr (kCopy) {
+      const int w = warp - (kFirstComputeWarp + 8);     // feature block of the tile this warp moves
+      const int64_t ntiles = a.Mp / kTileM;
+      uint32_t cp_ph = 0u;                              // bit t = phase of bar_cp(t)
+      auto copy_tile = [&](int t, uint8_t* dst, int nfb) {
+        mbar_wait(bar_cp(t), (cp_ph >> t) & 1u, 960 + t);
+        cp_ph ^= 1u << t;
+#ifdef NERF_DBG_NOCOPY       // timing experiment only (nothing is saved): what does the copy-out traffic cost?
+        if (false) {
+#else
+        if (w < nfb) {
+#endif
+          const uint8_t* sp = smem + kOffAct + t * kActBytes + w * 16384 + lane * 16;
+          uint8_t* dp = dst + w * 16384 + lane * 16;
+#pragma unroll 1
+          for (int i0 = 0; i0 < 32; i0 += 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(sp + (i0 + i) * 512);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(dp + (i0 + i) * 512) = v[i];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_cpfree(t));
+      };
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        const int64_t tile0 = ((int64_t)unit * kCtas + rank) * 2;
+        if constexpr (kBwd) {
+          for (int t = 0; t < 2; ++t) copy_tile(t, a.dhv_img + (tile0 + t) * 32768, 2);
+          for (int g = 0; g < kNumGemmsBwd; ++g) {
+            const int dst = (g == 0) ? 8 : 8 - g;
+            for (int t = 0; t < 2; ++t) copy_tile(t, a.dpre_img + ((int64_t)dst * ntiles + tile0 + t) * 65536, 4);
+          }
+        } else {
+          for (int g = 0; g < 9; ++g)
+            for (int t = 0; t < 2; ++t) copy_tile(t, a.act_img + ((int64_t)g * ntiles + tile0 + t) * 65536, 4);
+        }
+      }
+    }
   } else {
     // ================= prologue + epilogue warps =================
     // Group h (warps 3-6 / 7-10) owns the PROLOGUE of tile h (one row per thread).  Every EPILOGUE is
@@ -634,6 +692,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
     auto act_arrive = [&](int t) {
       if (kArriveLanes == 32) { __syncwarp(); if (lane != 0) return; }
       if (kCtas == 2 && rank != 0) mbar_arrive_cluster(mapa(bar_act(t), 0)); else mbar_arrive(bar_act(t));
+    };
+    // copy-out handshake (kCopy): request after the tile is complete + fenced, wait before the tile is written again
+    uint32_t cp_pend = 0u, cpfree_ph = 0u;            // bit t: a copy of tile t is outstanding / phase of bar_cpfree(t)
+    auto cp_request = [&](int t) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_cp(t));
+      cp_pend |= 1u << t;
+    };
+    auto cp_wait_free = [&](int t) {
+      if (cp_pend & (1u << t)) {
+        mbar_wait(bar_cpfree(t), (cpfree_ph >> t) & 1u, 970 + t);
+        cpfree_ph ^= 1u << t;
+        cp_pend &= ~(1u << t);
+      }
     };
     uint32_t acc_ph = 0u;                             // bit t = phase of bar_acc(t)
     const int64_t ntiles = a.Mp / kTileM;
@@ -690,6 +762,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             mbar_wait(bar_acc(t), (acc_ph >> t) & 1u, 400 + t);
             acc_ph ^= 1u << t;
             tc_fence_after();
+            if (kCopy) cp_wait_free(t);                        // the previous tensor of this tile has left shared memory
             TRACE(tw, tr_ok, 4 + 8 * t);
             DBG_T(t1_);
             DBG_ACC(0, t1_ - t0_);
@@ -721,7 +794,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
 #pragma unroll
                   for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), head[c0 + j], sigma);
                 }
+#ifndef NERF_DBG_NOMASK      // timing experiment only (no ReLU masks are saved)
                 if (kSave) mkw[mi] = relu_mask32(r);
+#endif
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                   uint4 o;
@@ -754,9 +829,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
                   chunk(rb, cb + c0 + 32, (c0 >> 5) + 1);
                 }
               }
+#ifndef NERF_DBG_NOMASK
               if (kSave && g < 8 && valid)
                 *reinterpret_cast<uint4*>(a.mask + ((int64_t)g * a.M + row) * 8 + 4 * ch) =
                     make_uint4(mkw[0], mkw[1], mkw[2], mkw[3]);
+#endif
              }
               tc_fence_before();
               fence_proxy_async();
@@ -767,7 +844,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
               DBG_ACC(1, t2_ - t1_);
               DBG_ACC(3, 1);
               if (g == 7) { if (t) sigma1 = sigma; else sigma0 = sigma; }
-              if (kSave) {                                 // off the critical path: the MMAs are already released
+              if (kSave && kCopy) cp_request(t);          // the copy warps move the tile to the workspace
+              if (kSave && !kCopy) {                       // off the critical path: the MMAs are already released
 #pragma unroll 1
                 for (int ch = ch_lo; ch < ch_hi; ++ch)
                   store_blocks(a.act_img + ((int64_t)g * ntiles + tile) * 65536, 2 * ch, at, 2 * ch, 2);
@@ -875,10 +953,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           const bool valid = row < a.M;
           uint8_t* at = smem + kOffAct + h * kActBytes;
           const float4 dr = valid ? __ldg(reinterpret_cast<const float4*>(a.d_raw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kCopy) { cp_wait_free(0); cp_wait_free(1); }     // the previous unit's last tensors have left shared memory
           if (kShared) {
             act_arrive(1 - h);
             // blocks 0-1 of tile 1 were copied out by the group-0 warps in the previous unit's last epilogue
-            named_bar_sync(1, 256);
+            if (!kCopy) named_bar_sync(1, 256);
           }
           uint4 mw = valid ? __ldg(reinterpret_cast<const uint4*>(a.hvmask) + row) : make_uint4(0u, 0u, 0u, 0u);
           const uint32_t mws[4] = {mw.x, mw.y, mw.z, mw.w};
@@ -900,8 +979,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
           fence_proxy_async();
           // copy d_hv out BEFORE releasing the MMAs: in the first epilogue warp (q,0) overwrites blocks 0-1 of
           // both tiles, and for tile 1 that is not the warp that copies here
-          if (kShared) store_blocks(a.dhv_img + (tile0 + h) * 32768, 0, at, 0, 2);
+          if (kShared && !kCopy) store_blocks(a.dhv_img + (tile0 + h) * 32768, 0, at, 0, 2);
           act_arrive(h);
+          if (kCopy) { cp_request(0); cp_request(1); }         // d_hv of both tiles (every warp arrives on both barriers)
           if (!kShared) store_blocks(a.dhv_img + (tile0 + h) * 32768, 0, at, 0, 2);
         }
         {
@@ -931,6 +1011,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             mbar_wait(bar_acc(t), (acc_ph >> t) & 1u, 400 + t);
             acc_ph ^= 1u << t;
             tc_fence_after();
+            if (kCopy) cp_wait_free(t);
             TRACE(tw, tr_ok, 4 + 8 * t);
             DBG_T(t1_);
             DBG_ACC(0, t1_ - t0_);
@@ -980,8 +1061,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcArgs a) {
             DBG_T(t2_);
             DBG_ACC(1, t2_ - t1_);
             DBG_ACC(3, 1);
+            if (kCopy) cp_request(t);
 #pragma unroll 1
-            for (int ch = ch_lo; ch < ch_hi; ++ch)
+            for (int ch = ch_lo; ch < ch_hi && !kCopy; ++ch)
               store_blocks(a.dpre_img + ((int64_t)dst * ntiles + tile) * 65536, 2 * ch, at, 2 * ch, 2);
             TRACE(tw, tr_ok, 6 + 8 * t);
             DBG_T(t3_);
@@ -1045,7 +1127,7 @@ static int launch_tc_impl(const TcArgs& a, cudaStream_t st) {
   const int grid = (units < max_units ? units : max_units) * kCtas;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3((unsigned)tc_threads<kBwd || kSave>());
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -227,11 +227,165 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
                     d_depth != nullptr ? d_depth[r] : 0.f, d_acc != nullptr ? d_acc[r] : 0.f, d_weights, d_raw, lane);
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-resident compositing for S <= 32 * NB (NB <= 8, i.e. every sampling of BASELINE.json except the 256+256
+// stress): the ray's samples are loaded ONCE -- all NB coalesced float4 loads of a lane are issued before the first one
+// is used, so a warp keeps NB * 512 B in flight instead of one block -- and the per-sample terms stay in registers,
+// which lets the analytic backward run from them without reading `raw` again (the generic backward above sweeps the
+// ray twice and the fused training kernel used to read it three times).  Arithmetic, operation order and the fp64
+// scans are those of composite_fwd_ray / composite_bwd_ray: the forward is bit-identical to the generic path, the
+// backward differs only in the association of d_sigma = d_alpha * (dist * e).
+// ------------------------------------------------------------------------------------------
+template <int NB>
+struct RayRegs {
+  float cr[NB], cg[NB], cb[NB];     // sigmoid(raw rgb)
+  float alpha[NB], om[NB];          // alpha, (1 - alpha) + 1e-10
+  float de[NB];                     // dist * exp(-sigma' dist), 0 where sigma' <= 0 (d alpha / d sigma)
+  float T[NB], z[NB];               // exclusive transmittance, sample depth
+};
+
+template <int NB, bool kKeep>
+__device__ __forceinline__ RayMaps composite_fwd_regs(const float4* __restrict__ raw, const float* __restrict__ z_vals,
+                                                      const float* __restrict__ rays_d, const float* __restrict__ noise,
+                                                      int r, int S, int white_bkgd, float* __restrict__ weights, int lane,
+                                                      RayRegs<NB>& st) {
+  const int64_t base = (int64_t)r * S;
+  float4 rw[NB];
+  float zz[NB], nz[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {                         // every load of the ray in flight before the first use
+    const int s = 32 * k + lane;
+    const bool valid = s < S;
+    rw[k] = valid ? __ldg(raw + base + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+    zz[k] = valid ? z_vals[base + s] : 0.f;
+    nz[k] = (noise != nullptr && valid) ? noise[base + s] : 0.f;
+  }
+  const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+  const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  double carry = 1.0;
+  float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const int s = 32 * k + lane;
+    const bool valid = s < S;
+    float z_nxt = __shfl_down_sync(0xffffffffu, zz[k], 1);
+    const float z_n0 = __shfl_sync(0xffffffffu, (k + 1 < NB) ? zz[k + 1] : 0.f, 0);
+    if (lane == 31) z_nxt = z_n0;
+    const SampleTerms t = sample_terms(rw[k], nz[k], zz[k], z_nxt, s == S - 1, dnorm);
+    const double p = warp_scan_mul(valid ? (double)t.om : 1.0, lane);
+    const double incl = carry * p;
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = carry;
+    carry = __shfl_sync(0xffffffffu, incl, 31);
+    const float T = (float)excl;                  // fp32(cumprod in double), exclusive       :147
+    const float w = valid ? __fmul_rn(t.alpha, T) : 0.f;                                   // :148
+    if (weights != nullptr && valid) weights[base + s] = w;
+    ar += __fmul_rn(w, t.r);                                                               // :151
+    ag += __fmul_rn(w, t.g);
+    ab += __fmul_rn(w, t.b);
+    ad += __fmul_rn(w, zz[k]);                                                             // :154
+    aa += w;                                                                               // :157
+    if (kKeep) {
+      st.cr[k] = t.r; st.cg[k] = t.g; st.cb[k] = t.b;
+      st.alpha[k] = valid ? t.alpha : 0.f; st.om[k] = t.om;
+      st.de[k] = (t.sig > 0.f) ? t.dist * t.e : 0.f;
+      st.T[k] = T; st.z[k] = zz[k];
+    }
+  }
+  ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aa = warp_sum(aa);
+  if (white_bkgd) {                                                                        // :160-161
+    const float bg = 1.f - aa;
+    ar += bg; ag += bg; ab += bg;
+  }
+  return RayMaps{ar, ag, ab, ad, aa};
+}
+
+// analytic backward from the kept terms (same formulas and fp64 sums as composite_bwd_ray)
+template <int NB>
+__device__ __forceinline__ void composite_bwd_regs(const RayRegs<NB>& st, int r, int S, int white_bkgd, float gR, float gG,
+                                                   float gB, float gD, float gA, const float* __restrict__ d_weights,
+                                                   float4* __restrict__ d_raw, int lane) {
+  const int64_t base = (int64_t)r * S;
+  if (white_bkgd) gA -= (gR + gG + gB);   // rgb_map += 1 - acc
+  float g[NB];
+  double total = 0.0;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const int s = 32 * k + lane;
+    const bool valid = s < S;
+    const float w = st.alpha[k] * st.T[k];
+    g[k] = gR * st.cr[k] + gG * st.cg[k] + gB * st.cb[k] + gD * st.z[k] + gA;
+    if (d_weights != nullptr && valid) g[k] += d_weights[base + s];
+    total += valid ? (double)w * (double)g[k] : 0.0;
+  }
+  total = warp_sum(total);
+  double prefix = 0.0;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const int s = 32 * k + lane;
+    const bool valid = s < S;
+    const float w = st.alpha[k] * st.T[k];
+    const double wg = valid ? (double)w * (double)g[k] : 0.0;
+    const double pin = warp_scan_add(wg, lane) + prefix;   // inclusive prefix of w*g
+    prefix = __shfl_sync(0xffffffffu, pin, 31);
+    const double suffix = total - pin;                     // sum_{k>i} w_k g_k
+    // suffix / om without a double-precision division (~30 instructions per sample): fp32 reciprocal + one fp64
+    // Newton step (relative error ~1e-14, far below the final rounding to fp32)
+    const float rf = __frcp_rn(st.om[k]);
+    const double q0 = suffix * (double)rf;
+    const double q = fma(q0, fma(-(double)st.om[k], (double)rf, 1.0), q0);
+    const float d_alpha = (float)((double)st.T[k] * (double)g[k] - q);
+    if (valid) {
+      float4 o;
+      o.x = w * gR * st.cr[k] * (1.f - st.cr[k]);
+      o.y = w * gG * st.cg[k] * (1.f - st.cg[k]);
+      o.z = w * gB * st.cb[k] * (1.f - st.cb[k]);
+      o.w = d_alpha * st.de[k];
+      d_raw[base + s] = o;
+    }
+  }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_fwd_regs_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
+                          const float* __restrict__ rays_d, const float* __restrict__ noise, int R, int S,
+                          int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ depth_map,
+                          float* __restrict__ acc_map, float* __restrict__ weights) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  RayRegs<NB> st;
+  const RayMaps m = composite_fwd_regs<NB, false>(raw, z_vals, rays_d, noise, r, S, white_bkgd, weights, lane, st);
+  if (lane == 0) {
+    rgb_map[3 * r] = m.r; rgb_map[3 * r + 1] = m.g; rgb_map[3 * r + 2] = m.b;
+    depth_map[r] = m.depth;
+    acc_map[r] = m.acc;
+  }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_bwd_regs_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
+                          const float* __restrict__ rays_d, const float* __restrict__ noise, int R, int S,
+                          int white_bkgd, const float* __restrict__ d_rgb, const float* __restrict__ d_depth,
+                          const float* __restrict__ d_acc, const float* __restrict__ d_weights,
+                          float4* __restrict__ d_raw) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  RayRegs<NB> st;
+  composite_fwd_regs<NB, true>(raw, z_vals, rays_d, noise, r, S, white_bkgd, nullptr, lane, st);
+  composite_bwd_regs<NB>(st, r, S, white_bkgd, d_rgb[3 * r], d_rgb[3 * r + 1], d_rgb[3 * r + 2],
+                         d_depth != nullptr ? d_depth[r] : 0.f, d_acc != nullptr ? d_acc[r] : 0.f, d_weights, d_raw, lane);
+}
+
 // Training pass of the FINE samples in one launch (scripts/train.py:374-382 around renderer.py:106-107):
 // composite -> rgb_map; d_rgb = 2 (rgb - target) / (3R) (the gradient of mean((rgb-target)^2), :376);
 // analytic backward -> d_raw; loss as a deterministic two-level fp64 reduction (per-block partials in
 // `scratch`, summed in block order by the last block to finish); and, folded in because this is the
 // last launch before the weight-gradient kernels, optimizer.zero_grad() of the flat gradient buffer.
+template <int NB>      // NB > 0: register-resident ray (S <= 32 NB, one read of raw); NB = 0: generic three-sweep path
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_train_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals, const float* __restrict__ rays_d,
                        const float* __restrict__ noise, int R, int S, int white_bkgd, const float* __restrict__ target,
@@ -246,7 +400,9 @@ composite_train_kernel(const float4* __restrict__ raw, const float* __restrict__
   const int r = blockIdx.x * kWarpsPerBlock + warp;
   double sq = 0.0;
   if (r < R) {
-    const RayMaps m = composite_fwd_ray(raw, z_vals, rays_d, noise, r, S, white_bkgd, nullptr, lane);
+    RayRegs<(NB > 0 ? NB : 1)> st;
+    const RayMaps m = (NB > 0) ? composite_fwd_regs<(NB > 0 ? NB : 1), true>(raw, z_vals, rays_d, noise, r, S, white_bkgd, nullptr, lane, st)
+                               : composite_fwd_ray(raw, z_vals, rays_d, noise, r, S, white_bkgd, nullptr, lane);
     const float scale = 2.f / (float)(3 * (int64_t)R);
     const float e0 = m.r - target[3 * r], e1 = m.g - target[3 * r + 1], e2 = m.b - target[3 * r + 2];
     sq = (double)e0 * (double)e0 + (double)e1 * (double)e1 + (double)e2 * (double)e2;
@@ -255,8 +411,11 @@ composite_train_kernel(const float4* __restrict__ raw, const float* __restrict__
       depth_map[r] = m.depth;
       acc_map[r] = m.acc;
     }
-    composite_bwd_ray(raw, z_vals, rays_d, noise, r, S, white_bkgd, scale * e0, scale * e1, scale * e2, 0.f, 0.f, nullptr,
-                      d_raw, lane);
+    if (NB > 0)
+      composite_bwd_regs<(NB > 0 ? NB : 1)>(st, r, S, white_bkgd, scale * e0, scale * e1, scale * e2, 0.f, 0.f, nullptr, d_raw, lane);
+    else
+      composite_bwd_ray(raw, z_vals, rays_d, noise, r, S, white_bkgd, scale * e0, scale * e1, scale * e2, 0.f, 0.f, nullptr,
+                        d_raw, lane);
   }
   if (lane == 0) part[warp] = sq;
   __syncthreads();
@@ -301,6 +460,53 @@ struct PdfArgs {
   int R, NB, N_imp, S_c;
   float* samples; int64_t* inds; float* cdf_out; float* z_fine;
 };
+
+// Bitonic sort of 32 * EPL values held in registers (value i of the sequence = element i % EPL of lane i / EPL):
+// compare-exchange partners closer than EPL are in the same lane, the others one __shfl_xor away -- no shared-memory
+// round trips and no __syncwarp per stage (the shared-memory network below spent 69 % of its time in the LSU pipe).
+// min / max of a pair keeps the multiset, so the result equals torch.sort's values bit for bit.
+template <int EPL>
+__device__ __forceinline__ void bitonic_regs(float (&e)[EPL], int lane) {
+  constexpr int N = 32 * EPL;
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= EPL) {
+        const int lm = stride / EPL;
+        const bool lower = (lane & lm) == 0;                 // this element is the lower index of its pair
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          const bool up = ((lane * EPL + j) & size) == 0;
+          const float o = __shfl_xor_sync(0xffffffffu, e[j], lm);
+          e[j] = (lower == up) ? fminf(e[j], o) : fmaxf(e[j], o);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          if ((j & stride) == 0) {
+            const bool up = ((lane * EPL + j) & size) == 0;
+            const float x = e[j], y = e[j | stride];
+            const float lo = fminf(x, y), hi = fmaxf(x, y);
+            e[j] = up ? lo : hi;
+            e[j | stride] = up ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void sort_in_regs(float* buf, int n, int lane) {      // buf[0 .. 32 * EPL): n values, rest ignored
+  float e[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) { const int i = lane * EPL + j; e[j] = i < n ? buf[i] : CUDART_INF_F; }
+  __syncwarp();
+  bitonic_regs<EPL>(e, lane);
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) buf[lane * EPL + j] = e[j];
+  __syncwarp();
+}
 
 template <bool kMerge>
 __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(PdfArgs a) {
@@ -388,10 +594,24 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(PdfArgs a) {
     if (sorted_in) {
       int npad = 64;
       while (npad < a.N_imp) npad <<= 1;
-      for (int k = a.N_imp + lane; k < npad; k += 32) sortbuf[k] = CUDART_INF_F;
       for (int k = lane; k < a.S_c; k += 32) zc[k] = z[k];
       __syncwarp();
-      bitonic(sortbuf, npad);
+      // the samples are already in order when u is (the deterministic linspace of render(), renderer.py:179) and no
+      // rounding inverted a pair: nothing to sort then
+      bool in_order = true;
+      for (int k = lane; k + 1 < a.N_imp; k += 32)
+        if (sortbuf[k + 1] < sortbuf[k]) in_order = false;
+      in_order = __all_sync(0xffffffffu, in_order);
+      if (!in_order) {
+        if (npad == 64) sort_in_regs<2>(sortbuf, a.N_imp, lane);
+        else if (npad == 128) sort_in_regs<4>(sortbuf, a.N_imp, lane);
+        else if (npad == 256) sort_in_regs<8>(sortbuf, a.N_imp, lane);
+        else {
+          for (int k = a.N_imp + lane; k < npad; k += 32) sortbuf[k] = CUDART_INF_F;
+          __syncwarp();
+          bitonic(sortbuf, npad);
+        }
+      }
       for (int i = lane; i < a.S_c; i += 32) {       // rank of a coarse depth among the samples: #{j : zs[j] < a}
         const float v = zc[i];
         int lo = 0, hi = a.N_imp;
@@ -488,8 +708,15 @@ extern "C" int nerf_composite_fwd(const float* raw, const float* z_vals, const f
   NERF_CHECK_ARG(R >= 0 && S >= 1, "nerf_composite_fwd: bad shape R=%d S=%d", R, S);
   NERF_CHECK_ARG(((uintptr_t)raw & 15) == 0, "nerf_composite_fwd: raw must be 16-byte aligned");
   if (R == 0) return 0;
-  composite_fwd_kernel<<<ceil_div(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      (const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, rgb_map, depth_map, acc_map, weights);
+  const dim3 grid(ceil_div(R, kWarpsPerBlock)), block(kWarpsPerBlock * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+#define NERF_FWD_NB(nb) composite_fwd_regs_kernel<nb><<<grid, block, 0, st>>>((const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, rgb_map, depth_map, acc_map, weights)
+  if (S <= 64) NERF_FWD_NB(2);
+  else if (S <= 128) NERF_FWD_NB(4);
+  else if (S <= 192) NERF_FWD_NB(6);
+  else if (S <= 256) NERF_FWD_NB(8);
+  else composite_fwd_kernel<<<grid, block, 0, st>>>((const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, rgb_map, depth_map, acc_map, weights);
+#undef NERF_FWD_NB
   NERF_LAUNCH_CHECK("composite_fwd_kernel");
   return 0;
 }
@@ -501,9 +728,15 @@ extern "C" int nerf_composite_bwd(const float* raw, const float* z_vals, const f
   NERF_CHECK_ARG(R >= 0 && S >= 1, "nerf_composite_bwd: bad shape R=%d S=%d", R, S);
   NERF_CHECK_ARG((((uintptr_t)raw | (uintptr_t)d_raw) & 15) == 0, "nerf_composite_bwd: raw/d_raw must be 16-byte aligned");
   if (R == 0) return 0;
-  composite_bwd_kernel<<<ceil_div(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      (const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, d_rgb_map, d_depth, d_acc, d_weights,
-      (float4*)d_raw);
+  const dim3 grid(ceil_div(R, kWarpsPerBlock)), block(kWarpsPerBlock * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+#define NERF_BWD_NB(nb) composite_bwd_regs_kernel<nb><<<grid, block, 0, st>>>((const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, d_rgb_map, d_depth, d_acc, d_weights, (float4*)d_raw)
+  if (S <= 64) NERF_BWD_NB(2);
+  else if (S <= 128) NERF_BWD_NB(4);
+  else if (S <= 192) NERF_BWD_NB(6);
+  else if (S <= 256) NERF_BWD_NB(8);
+  else composite_bwd_kernel<<<grid, block, 0, st>>>((const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, d_rgb_map, d_depth, d_acc, d_weights, (float4*)d_raw);
+#undef NERF_BWD_NB
   NERF_LAUNCH_CHECK("composite_bwd_kernel");
   return 0;
 }
@@ -522,9 +755,15 @@ extern "C" int nerf_composite_train(const float* raw, const float* z_vals, const
   NERF_CHECK_ARG((((uintptr_t)raw | (uintptr_t)d_raw | (uintptr_t)zero_buf) & 15) == 0 && ((uintptr_t)scratch & 7) == 0,
                  "nerf_composite_train: raw/d_raw/zero_buf must be 16-byte aligned, scratch 8-byte aligned");
   NERF_CHECK_ARG(zero_n >= 0 && (zero_n & 3) == 0, "nerf_composite_train: zero_n must be a multiple of 4 (got %lld)", (long long)zero_n);
-  composite_train_kernel<<<ceil_div(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      (const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, target, rgb_map, depth_map, acc_map, (float4*)d_raw, loss,
-      (double*)scratch, (float4*)zero_buf, zero_buf != nullptr ? zero_n / 4 : 0);
+  const dim3 grid(ceil_div(R, kWarpsPerBlock)), block(kWarpsPerBlock * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+#define NERF_TRAIN_NB(nb) composite_train_kernel<nb><<<grid, block, 0, st>>>((const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, target, rgb_map, depth_map, acc_map, (float4*)d_raw, loss, (double*)scratch, (float4*)zero_buf, zero_buf != nullptr ? zero_n / 4 : 0)
+  if (S <= 64) NERF_TRAIN_NB(2);
+  else if (S <= 128) NERF_TRAIN_NB(4);
+  else if (S <= 192) NERF_TRAIN_NB(6);
+  else if (S <= 256) NERF_TRAIN_NB(8);
+  else NERF_TRAIN_NB(0);
+#undef NERF_TRAIN_NB
   NERF_LAUNCH_CHECK("composite_train_kernel");
   return 0;
 }

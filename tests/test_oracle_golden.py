@@ -279,7 +279,10 @@ def test_ref_build_is_bytecode_only():
     """oracle/_ref holds compiled modules only -- no reference source is copied into the tree -- and is git-ignored."""
     from oracle import build_ref
     _ref_or_skip()
-    files = sorted(os.listdir(os.path.join(build_ref.OUT, "nerfmlp")))
-    assert files and all(f.endswith(".pyc") or f == "__pycache__" for f in files), files
+    import zipfile
+    with zipfile.ZipFile(build_ref.ARCHIVE) as z:
+        files = sorted(z.namelist())
+    assert files and all(f.endswith(".pyc") or f == "BUILD_INFO.txt" for f in files), files
+    assert not any(f.endswith(".py") for f in os.listdir(build_ref.OUT))
     gi = open(os.path.join(os.path.dirname(build_ref.HERE), ".gitignore")).read()
     assert "oracle/_ref/" in gi
