@@ -866,7 +866,7 @@ def main():
         rec = dp_parity(cx, args)
         if rank == 0:
             emit({"dp_parity": rec})
-        td.destroy_process_group()
+        finish(world)
         return
 
     common = {"n_gpus": world, "higher_is_better": True, "vs_baseline": None, "dtype": args.precision, "data": "synthetic"}
@@ -915,8 +915,20 @@ def main():
             line["torch_eager_gpu"] = {"unavailable": repr(exc)[:200]}
     if rank == 0:
         emit(line)
+    finish(world)
+
+
+def finish(world):
+    """Leave a multi-rank run without tearing the process group down: destroy_process_group() with CUDA graphs that hold
+    captured NCCL kernels still alive was seen to hang after the result line had been printed (the line is out, every
+    rank has passed the last barrier, nothing is left to flush), so the ranks exit hard with status 0."""
     if world > 1:
-        td.destroy_process_group()
+        import torch
+        import torch.distributed as td
+        td.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

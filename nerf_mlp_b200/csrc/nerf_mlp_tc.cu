@@ -333,6 +333,10 @@ struct TcArgs {
   uint8_t* dpre_img; uint8_t* dhv_img;
   int64_t Mp;                       // rows padded to whole tile pairs
   int num_pairs;
+  // work units: units [0, n_full_units) hold two tiles per CTA; the units after them ("half units", at most one per
+  // CTA, always a CTA's last) hold ONE tile per CTA -- the tiles of a last partial wave are spread over twice as many
+  // SMs instead of leaving most of them idle for a whole unit (196 608 rows = 5.19 waves of 148 x 2 tiles)
+  int n_full_units, n_units;
 };
 
 // bf16 x-tile row: 63 encoded channels (+ a zero pad column) -> 8 swizzled 16-byte chunks
@@ -426,7 +430,13 @@ __global__ void __launch_bounds__((tc_threads<kBwd || kSave>()), 1) mlp_tc_kerne
   const uint32_t rank = (kCtas == 2) ? cluster_ctarank() : 0u;
   const int unit0 = (kCtas == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work unit of this CTA (pair)
   const int unit_step = (kCtas == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int num_units = (kCtas == 2) ? (a.num_pairs + 1) / 2 : a.num_pairs;      // unit = tile pair (1 CTA) / quad (CTA pair)
+  const int num_units = a.n_units;                                                  // unit = tile pair (1 CTA) / quad (CTA pair); half units last
+  // first tile of this CTA in `unit`, and how many tiles (2, or 1 in a half unit) it has there
+  auto unit_tiles = [&](int unit, int64_t& tile0) -> int {
+    if (unit < a.n_full_units) { tile0 = ((int64_t)unit * kCtas + rank) * 2; return 2; }
+    tile0 = (int64_t)a.n_full_units * kCtas * 2 + (int64_t)(unit - a.n_full_units) * kCtas + rank;
+    return 1;
+  };
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
@@ -538,9 +548,22 @@ __global__ void __launch_bounds__((tc_threads<kBwd || kSave>()), 1) mlp_tc_kerne
       // first epilogue has finished, i.e. half a period of the (now independent) per-tile chains
       if (t == 1) mbar_wait(bar_skew, 0, 500);
       for (int unit = unit0; unit < num_units; unit += unit_step) {
+        const bool idle = (t == 1) && unit >= a.n_full_units;      // half unit: tile B does not exist
         for (int i = 0; i < nslots; ++i) {
           const uint4 rec = *reinterpret_cast<const uint4*>(&c_slots[slot0 + i]);
           const uint32_t a_add = rec.z, fl = rec.w;
+          if (idle) {
+            // keep the ring protocol (a slot is freed by BOTH issuers) without issuing: an empty commit arrives at once
+            mbar_wait(bar_full(s), ph, 200 + (int)s);
+            if (kCtas == 2 && NERF_TC_RELAY_FULL == 0) mbar_wait(bar_pfull(s), ph, 220 + (int)s);
+            tc_fence_after();
+            if (elect_one()) {
+              if (kCtas == 2) tc_commit_mc2(bar_empty(s), 3); else tc_commit(bar_empty(s));
+            }
+            __syncwarp();
+            if (++s == s_hi) { s = s_lo; ph ^= 1; }
+            continue;
+          }
 #ifdef NERF_DBG_TIMING
           const long long i0_ = clock64();
 #endif
@@ -635,16 +658,18 @@ __global__ void __launch_bounds__((tc_threads<kBwd || kSave>()), 1) mlp_tc_kerne
         if (lane == 0) mbar_arrive(bar_cpfree(t));
       };
       for (int unit = unit0; unit < num_units; unit += unit_step) {
-        const int64_t tile0 = ((int64_t)unit * kCtas + rank) * 2;
+        int64_t tile0;
+        const int ntl = unit_tiles(unit, tile0);
         if constexpr (kBwd) {
-          for (int t = 0; t < 2; ++t) copy_tile(t, a.dhv_img + (tile0 + t) * 32768, 2);
+          for (int t = 0; t < ntl; ++t) copy_tile(t, a.dhv_img + (tile0 + t) * 32768, 2);
           for (int g = 0; g < kNumGemmsBwd; ++g) {
             const int dst = (g == 0) ? 8 : 8 - g;
-            for (int t = 0; t < 2; ++t) copy_tile(t, a.dpre_img + ((int64_t)dst * ntiles + tile0 + t) * 65536, 4);
+            for (int t = 0; t < ntl; ++t) copy_tile(t, a.dpre_img + ((int64_t)dst * ntiles + tile0 + t) * 65536, 4);
           }
         } else {
           for (int g = 0; g < 9; ++g)
-            for (int t = 0; t < 2; ++t) copy_tile(t, a.act_img + ((int64_t)g * ntiles + tile0 + t) * 65536, 4);
+            for (int t = 0; t < ntl; ++t)
+              copy_tile(t, a.act_img + ((int64_t)g * ntiles + tile0 + t) * 65536, 4);
         }
       }
     }
@@ -717,7 +742,9 @@ __global__ void __launch_bounds__((tc_threads<kBwd || kSave>()), 1) mlp_tc_kerne
     // (Not the x-tile: with NERF_TC_PIPE_PROLOGUE it already holds the next unit's encoding by then.)
     auto xchg_of = [&](int t) { return reinterpret_cast<float4*>(smem + kOffAct + t * kActBytes + 3 * 16384 + q * 1024); };
     for (int unit = unit0; unit < num_units; unit += unit_step) {
-      const int64_t tile0 = ((int64_t)unit * kCtas + rank) * 2;
+      int64_t tile0;
+      const int ntl = unit_tiles(unit, tile0);               // 2 tiles, or 1 in a half unit (tile B and its group's prologue idle)
+      const bool own = h < ntl;                              // this warp group's own tile (prologue) exists
 #ifdef NERF_DBG_TRACE
       const int tw = (warp == kFirstComputeWarp) ? 2 : 3;
       const bool tr_ok = (warp == kFirstComputeWarp || warp == kFirstComputeWarp + 4) && lane == 0 && unit == unit0 + 2 * unit_step;
@@ -733,17 +760,19 @@ __global__ void __launch_bounds__((tc_threads<kBwd || kSave>()), 1) mlp_tc_kerne
           //  arrives were made right after each tile's last epilogue, so tile A's layer 0 runs under tile B's
           //  last epilogue)
           if (!kPipe || unit == unit0) {
-            if (kShared) act_arrive(1 - h);                // nothing to write for the other tile
-            fwd_prologue(a, row, m, xt_own);
-            fence_proxy_async();
-            act_arrive(h);
+            if (kShared && 1 - h < ntl) act_arrive(1 - h); // nothing to write for the other tile
+            if (own) {
+              fwd_prologue(a, row, m, xt_own);
+              fence_proxy_async();
+              act_arrive(h);
+            }
           }
-          if (kSave && (!kPipe || unit == unit0)) store_blocks(a.xenc_img + (tile0 + h) * 16384, 0, xt_own, 0, 1);
+          if (kSave && own && (!kPipe || unit == unit0)) store_blocks(a.xenc_img + (tile0 + h) * 16384, 0, xt_own, 0, 1);
         }
         float sigma0 = 0.f, sigma1 = 0.f;                  // partial sigma head of (tile A / B, own column half)
         for (int g = 0; g < kNumGemms; ++g) {
 #pragma unroll 1
-          for (int t = t_lo; t < t_hi; ++t) {
+          for (int t = t_lo; t < t_hi && t < ntl; ++t) {
             float sigma = t ? sigma1 : sigma0;
             const int64_t tile = tile0 + t;
             const int64_t row = tile * kTileM + m;
@@ -783,7 +812,8 @@ __global__ void __launch_bounds__((tc_threads<kBwd || kSave>()), 1) mlp_tc_kerne
               named_bar_sync(1, 256);
               if (h == 0 && valid)
                 *reinterpret_cast<float4*>(a.out + row * 4) = make_float4(0.f, 0.f, 0.f, sigma + xchg[lane].w + head[640]);
-              if (kPipe && unit + unit_step < num_units) act_arrive(t);     // next unit's layer 0 of this tile may start
+              if (kPipe && unit + unit_step < num_units && (t == 0 || unit + unit_step < a.n_full_units))
+                act_arrive(t);                                                // next unit's layer 0 of this tile may start
             } else if (g < 9) {
 #pragma unroll 1
              for (int ch = ch_lo; ch < ch_hi; ++ch) {
@@ -912,7 +942,8 @@ __global__ void __launch_bounds__((tc_threads<kBwd || kSave>()), 1) mlp_tc_kerne
                   *reinterpret_cast<float4*>(a.out + row * 4) =
                       make_float4(o0 + p.x + head[641], o1 + p.y + head[642], o2 + p.z + head[643], sigma + p.w + head[640]);
               }
-              if (kPipe && unit + unit_step < num_units) act_arrive(t);     // next unit's layer 0 of this tile may start
+              if (kPipe && unit + unit_step < num_units && (t == 0 || unit + unit_step < a.n_full_units))
+                act_arrive(t);                                                // next unit's layer 0 of this tile may start
               if (kSave) {
 #pragma unroll 1
                 for (int ch = ch_lo; ch < ch_hi; ++ch) store_blocks(a.hv_img + tile * 32768, ch, at, 2 * ch, 1);
@@ -938,10 +969,12 @@ __global__ void __launch_bounds__((tc_threads<kBwd || kSave>()), 1) mlp_tc_kerne
           if (kPipe && g == 5 && unit + unit_step < num_units) {
             // layer 5 was the x-tile's last reader (its MMAs completed before the accumulator barrier fired):
             // encode the next unit's points now, under the wait for the layer-6 accumulators
-            const int64_t tile0n = ((int64_t)(unit + unit_step) * kCtas + rank) * 2;
-            fwd_prologue(a, (tile0n + h) * kTileM + m, m, xt_own);
-            fence_proxy_async();
-            if (kSave) store_blocks(a.xenc_img + (tile0n + h) * 16384, 0, xt_own, 0, 1);
+            int64_t tile0n;
+            if (h < unit_tiles(unit + unit_step, tile0n)) {
+              fwd_prologue(a, (tile0n + h) * kTileM + m, m, xt_own);
+              fence_proxy_async();
+              if (kSave) store_blocks(a.xenc_img + (tile0n + h) * 16384, 0, xt_own, 0, 1);
+            }
           }
         }
       } else {
@@ -950,15 +983,16 @@ __global__ void __launch_bounds__((tc_threads<kBwd || kSave>()), 1) mlp_tc_kerne
         {
           // prologue (own tile): d_hv_pre = (d_rgb . W_rgb) * [hv > 0]  (reference autograd of model.py:73-75)
           const int64_t row = (tile0 + h) * kTileM + m;
-          const bool valid = row < a.M;
+          const bool valid = own && row < a.M;
           uint8_t* at = smem + kOffAct + h * kActBytes;
           const float4 dr = valid ? __ldg(reinterpret_cast<const float4*>(a.d_raw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
           if (kCopy) { cp_wait_free(0); cp_wait_free(1); }     // the previous unit's last tensors have left shared memory
           if (kShared) {
-            act_arrive(1 - h);
+            if (1 - h < ntl) act_arrive(1 - h);
             // blocks 0-1 of tile 1 were copied out by the group-0 warps in the previous unit's last epilogue
             if (!kCopy) named_bar_sync(1, 256);
           }
+          if (own) {
           uint4 mw = valid ? __ldg(reinterpret_cast<const uint4*>(a.hvmask) + row) : make_uint4(0u, 0u, 0u, 0u);
           const uint32_t mws[4] = {mw.x, mw.y, mw.z, mw.w};
 #pragma unroll
@@ -981,20 +1015,21 @@ __global__ void __launch_bounds__((tc_threads<kBwd || kSave>()), 1) mlp_tc_kerne
           // both tiles, and for tile 1 that is not the warp that copies here
           if (kShared && !kCopy) store_blocks(a.dhv_img + (tile0 + h) * 32768, 0, at, 0, 2);
           act_arrive(h);
-          if (kCopy) { cp_request(0); cp_request(1); }         // d_hv of both tiles (every warp arrives on both barriers)
-          if (!kShared) store_blocks(a.dhv_img + (tile0 + h) * 32768, 0, at, 0, 2);
+          }
+          if (kCopy) { cp_request(0); if (ntl > 1) cp_request(1); }   // d_hv of the unit's tiles (every warp arrives on each barrier)
+          if (!kShared && own) store_blocks(a.dhv_img + (tile0 + h) * 32768, 0, at, 0, 2);
         }
         {
           const int64_t r0 = tile0 * kTileM + m, r1 = r0 + kTileM;
           dsig0 = r0 < a.M ? __ldg(a.d_raw + r0 * 4 + 3) : 0.f;
-          dsig1 = r1 < a.M ? __ldg(a.d_raw + r1 * 4 + 3) : 0.f;
+          dsig1 = (ntl > 1 && r1 < a.M) ? __ldg(a.d_raw + r1 * 4 + 3) : 0.f;
         }
         for (int g = 0; g < kNumGemms; ++g) {
           // g = 0: d_bott (no mask) | g = 1: d_h7 (+ sigma term, mask 7) | g >= 2: d_pre_{8-g} (mask 8-g)
           const int ml = 8 - g;                                    // mask layer (g >= 1)
           const int dst = (g == 0) ? 8 : ml;                        // dpre slot: 8 = d_bott, else layer index
 #pragma unroll 1
-          for (int t = t_lo; t < t_hi; ++t) {
+          for (int t = t_lo; t < t_hi && t < ntl; ++t) {
             const float dsig = t ? dsig1 : dsig0;
             const int64_t tile = tile0 + t;
             const int64_t row = tile * kTileM + m;
@@ -1122,8 +1157,15 @@ static int launch_tc_impl(const TcArgs& a, cudaStream_t st) {
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<kBwd, kSave, kCtas, kSigmaOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done.mark(dp.ordinal);
   }
-  const int units = (kCtas == 2) ? (a.num_pairs + 1) / 2 : a.num_pairs;
-  const int max_units = dp.sm_count / kCtas;
+  const int max_units = dp.sm_count / kCtas;                  // CTAs (or CTA pairs) that run at once
+  const int units_all = (kCtas == 2) ? (a.num_pairs + 1) / 2 : a.num_pairs;   // as full units (two tiles per CTA)
+  // the last partial wave: if at most half of the CTAs would get a (two-tile) unit, hand out one-tile half units instead
+  const int rem = units_all % max_units;
+  TcArgs ah = a;
+  static const bool half_ok = [] { const char* e = getenv("NERF_TC_HALF_UNITS"); return !(e && e[0] == '0'); }();
+  if (half_ok && rem > 0 && 2 * rem <= max_units) { ah.n_full_units = units_all - rem; ah.n_units = units_all + rem; }
+  else { ah.n_full_units = units_all; ah.n_units = units_all; }
+  const int units = ah.n_units;
   const int grid = (units < max_units ? units : max_units) * kCtas;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -1135,7 +1177,7 @@ static int launch_tc_impl(const TcArgs& a, cudaStream_t st) {
   attr[0].val.clusterDim.x = kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (kCtas == 2) ? 1 : 0;
-  NERF_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<kBwd, kSave, kCtas, kSigmaOnly>, a));
+  NERF_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<kBwd, kSave, kCtas, kSigmaOnly>, ah));
   NERF_LAUNCH_CHECK(kBwd ? "mlp_tc_kernel<dgrad>" : "mlp_tc_kernel<fwd>");
   return 0;
 }
@@ -1205,6 +1247,7 @@ int mlp_tc_backward(const float* d_raw, int64_t M, int rows_per_dir, const float
   a.num_pairs = (int)(L.Mp / (2 * kTileM));   // the whole padded tile range: every tile image the wgrad kernel reads is written (single-CTA mode too)
   if (stage == NERF_BWD_ALL && bwd_fused_enabled()) {
     // one launch: dgrad chain + tensor-core weight gradients; the two tiny heads (rgb, sigma) follow on CUDA cores
+    if ((rc = mlp_tc_heads_fork(st))) return rc;                 // the heads run beside the big kernel (side stream)
     if ((rc = launch_bwd_fused(a, ws, L, grads, st))) return rc;
     return mlp_tc_heads_wgrad(ws, L, d_raw, M, grads, st);
   }

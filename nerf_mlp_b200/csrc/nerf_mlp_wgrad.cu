@@ -288,13 +288,48 @@ __global__ void __launch_bounds__(32 * kHeadsWarps) heads_wgrad_kernel(const flo
   }
 }
 
-// rgb / sigma head gradients alone (the fused backward kernel does everything else)
+// Internal side stream (one per device, created on first use) for the two tiny heads: they read tensors the big
+// backward kernel does not (hv, and h7 a second time) and fill its ramp-up / tail instead of adding 40 us after it.
+// Fork and join are event dependencies (capturable in a CUDA graph, no host synchronisation).
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static int side_stream(SideStream** out) {
+  static SideStream side[kMaxDevices];
+  DeviceProps dp;
+  int rc = current_device(&dp);
+  if (rc) return rc;
+  NERF_CHECK_ARG(dp.ordinal >= 0 && dp.ordinal < kMaxDevices, "device ordinal %d out of range", dp.ordinal);
+  SideStream& x = side[dp.ordinal];
+  if (x.s == nullptr) {
+    NERF_CUDA(cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking));
+    NERF_CUDA(cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming));
+    NERF_CUDA(cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming));
+  }
+  *out = &x;
+  return 0;
+}
+
+// rgb / sigma head gradients beside the fused backward kernel: call fork BEFORE launching the big kernel on `st`
+// (the heads only depend on what precedes it) and launch_join AFTER (the big kernel's CTAs take the SMs first; the
+// heads' blocks run wherever one of them has finished).
+int mlp_tc_heads_fork(cudaStream_t st) {
+  SideStream* x;
+  int rc = side_stream(&x);
+  if (rc) return rc;
+  NERF_CUDA(cudaEventRecord(x->fork, st));
+  NERF_CUDA(cudaStreamWaitEvent(x->s, x->fork, 0));
+  return 0;
+}
 int mlp_tc_heads_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t M, float* grads, cudaStream_t st) {
+  SideStream* x;
+  int rc = side_stream(&x);
+  if (rc) return rc;
   const uint8_t* b = (const uint8_t*)ws;
   const int64_t ntiles = L.Mp / kTileM;
-  heads_wgrad_kernel<<<ceil_div(M, (int64_t)kHeadsWarps * kHeadsRowsPerWarp), 32 * kHeadsWarps, 0, st>>>(
+  heads_wgrad_kernel<<<ceil_div(M, (int64_t)kHeadsWarps * kHeadsRowsPerWarp), 32 * kHeadsWarps, 0, x->s>>>(
       d_raw, b + L.hv, b + L.act + (int64_t)7 * ntiles * 65536, M, grads);
   NERF_LAUNCH_CHECK("heads_wgrad_kernel");
+  NERF_CUDA(cudaEventRecord(x->join, x->s));
+  NERF_CUDA(cudaStreamWaitEvent(st, x->join, 0));
   return 0;
 }
 
@@ -350,29 +385,11 @@ int mlp_tc_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t 
     nblocks += (int)s;
   }
   jb.n = nj;
-  // The two tiny heads run on CUDA cores and read tensors the tensor-core jobs do not (hv, and h7
-  // a second time); they are forked onto an internal side stream so that they fill the HBM-bound
-  // wgrad kernel's ramp-up / tail instead of adding 40 us after it.  Fork and join are event
-  // dependencies (capturable in a CUDA graph, no host synchronisation); stream and events are
-  // created once per device on the first call.
-  static cudaStream_t side[16] = {};
-  static cudaEvent_t ev_fork[16] = {}, ev_join[16] = {};
-  const int dev = dp.ordinal;
-  NERF_CHECK_ARG(dev >= 0 && dev < 16, "mlp_tc_wgrad: device ordinal %d out of range", dev);
-  if (side[dev] == nullptr) {
-    NERF_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
-    NERF_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
-    NERF_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
-  }
-  NERF_CUDA(cudaEventRecord(ev_fork[dev], st));
-  NERF_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
+  int rc2 = mlp_tc_heads_fork(st);
+  if (rc2) return rc2;
   wgrad_tc_kernel<<<nblocks, kWgThreads, kWgSmemBytes, st>>>(jb, L.Mp);
   NERF_LAUNCH_CHECK("wgrad_tc_kernel");
-  heads_wgrad_kernel<<<ceil_div(M, (int64_t)kHeadsWarps * kHeadsRowsPerWarp), 32 * kHeadsWarps, 0, side[dev]>>>(
-      d_raw, hv, ACT(7), M, grads);
-  NERF_LAUNCH_CHECK("heads_wgrad_kernel");
-  NERF_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
-  NERF_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
+  if ((rc2 = mlp_tc_heads_wgrad(ws, L, d_raw, M, grads, st))) return rc2;
   return 0;
 }
 

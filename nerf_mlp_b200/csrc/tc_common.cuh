@@ -101,6 +101,7 @@ inline WsLayout ws_layout(int64_t M, int save) {
 
 int mlp_tc_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t M, int rows_per_dir, float* grads,
                  cudaStream_t st);
+int mlp_tc_heads_fork(cudaStream_t st);
 int mlp_tc_heads_wgrad(const void* ws, const WsLayout& L, const float* d_raw, int64_t M, float* grads, cudaStream_t st);
 
 }  // namespace nerf
