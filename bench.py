@@ -474,10 +474,12 @@ def bench_train(cx, args, rays, K, W, full=True):
     h2d, d2h = 3 * rays * 12, (24 if not args.autograd else 4)
 
     # --- warm-up, then EXACTLY K timed steps (device time, per-step events, L2 flushed in between) ---
+    # (the clock sampler starts before the warm-up: nvidia-smi needs a few hundred ms to deliver its first sample and a
+    #  20-step timed region lasts ~20 ms; the warm-up steps run the same kernels at the same clocks)
+    sampler = ClockSampler(cx.local).start()
     for _ in range(W):
         run()
     cx.barrier()
-    sampler = ClockSampler(cx.local).start()
     launches0 = dll.nerf_launch_count()
     evs = []
     cx.barrier()
@@ -673,10 +675,10 @@ def bench_render(cx, args, total, K, W):
     timed_fwd.on = False
     ops.mlp_fwd_rays = timed_fwd
     try:
+        sampler = ClockSampler(cx.local).start()
         for _ in range(W):
             run()
         cx.barrier()
-        sampler = ClockSampler(cx.local).start()
         launches0 = dll.nerf_launch_count()
         timed_fwd.on = True
         evs = []

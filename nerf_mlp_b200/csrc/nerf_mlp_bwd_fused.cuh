@@ -34,7 +34,7 @@ constexpr int kFzOffA = 0, kFzOffB = 16384;
 constexpr int kFzBiasWarps = 2;
 constexpr int kFzCopyWarps = 2;
 #ifndef NERF_FZ_PREFETCH
-#define NERF_FZ_PREFETCH 6
+#define NERF_FZ_PREFETCH 0     // measured: 0.625 ms without, 0.641 ms with distance 6 (1024 rays x 192): the loads are not latency-bound
 #endif
 constexpr int kFzPrefetch = NERF_FZ_PREFETCH;     // L2 prefetch distance of the X operand, in 64-row chunks
 constexpr int kFzKindsC = 10;
@@ -275,7 +275,6 @@ __global__ void __launch_bounds__(kFzThreads, 1) bwd_fused_kernel(const __grid_c
       // written dY tiles out of L2 before their wgrad role gets to them; dY is dead after its last reader (layer 5 and
       // d_hv have two readers: normal priority there)
       const uint64_t pol_x = l2_policy_evict_first();
-      const bool x_hint = !(fa.dbg & 16);
       for (int c = 0; c < wg_chunks; ++c) {
         const int s = c % L::kStages;
         const int ti = c >> 1;
@@ -316,17 +315,13 @@ __global__ void __launch_bounds__(kFzThreads, 1) bwd_fused_kernel(const __grid_c
           const uint32_t sa = sbase + L::kOffWg + s * kFzStageBytes + kFzOffA, sb = sa + (kFzOffB - kFzOffA);
           const uint8_t* a_src = job.A + tile * job.a_tile_bytes;
           mbar_expect_tx(bar_wfull(s), bytes);
-          if (fa.dbg & 32) {      // development (WRONG RESULTS): the same bytes as ONE request, to see what the request count costs
-            bulk_g2s(sa, a_src, bytes, bar_wfull(s));
-          } else {
           for (int fb = 0; fb < 2; ++fb) {
             const uint8_t* src = a_src + (a_fb + fb) * 16384 + half;
             bulk_g2s(sa + fb * 8192, src, 8192, bar_wfull(s));
           }
           for (int fb = 0; fb < job.b_nfb; ++fb) {
             const uint8_t* src = job.B + tile * job.b_tile_bytes + (b_fb + fb) * 16384 + half;
-            if (x_hint) bulk_g2s_hint(sb + fb * 8192, src, 8192, bar_wfull(s), pol_x); else bulk_g2s(sb + fb * 8192, src, 8192, bar_wfull(s));
-          }
+            bulk_g2s_hint(sb + fb * 8192, src, 8192, bar_wfull(s), pol_x);
           }
         }
         __syncwarp();
@@ -663,7 +658,7 @@ static int launch_bwd_fused(const TcArgs& ta, void* ws, const WsLayout& L, float
   int first = 0;
   for (int j = 0; j < nj; ++j) { fa.jobs[j].first_pair = first; fa.jobs[j].npairs = alloc[j]; first += alloc[j]; }
   static const int dbg = [] { const char* e = getenv("NERF_FZ_MODE"); return e ? atoi(e) : 0; }();
-  static const int stagger = [] { const char* e = getenv("NERF_FZ_STAGGER"); return e ? atoi(e) : 1000; }();
+  static const int stagger = [] { const char* e = getenv("NERF_FZ_STAGGER"); return e ? atoi(e) : 0; }();   // measured: no gain from 1000 / 2000 clk
   fa.dbg = dbg;
   fa.grads = grads;
   for (int k = 0; k < 8; ++k) fa.db_off[k] = (int)b_off(k);

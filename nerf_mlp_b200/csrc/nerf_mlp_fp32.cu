@@ -160,8 +160,145 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Forward-layer SGEMM (the hot GEMMs of the check mode: C = relu(A W^T + b), A and W both K-contiguous, N >= 64):
+// 128 x 128 x 8 tiles, 8 x 8 outputs per thread, shared memory double-buffered with the next tile's global loads
+// held in registers while the current tile is multiplied (one __syncthreads per K-step of 8), 16-byte global loads
+// wherever the row pitch allows.  Plain FFMA in K order 0, 1, 2, ...: every output is the same fp32 dot product
+// the generic kernel computes (same summation order), so the two kernels are bit-identical.
+// (Round 1's generic kernel reached 18.5 TFLOP/s, slower than eager PyTorch on the same GPU.)
+// ------------------------------------------------------------------------------------------
+constexpr int FBK = 8;
+template <bool kVecA, bool kVecB>
+__global__ void __launch_bounds__(256, 2) sgemm_fwd_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[2][FBK][BM + 4];
+  __shared__ __align__(16) float Bs[2][FBK][BN + 4];
+  const int t = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int tx = t & 15, ty = t >> 4;
+  const int lrow = t >> 1, lk = (t & 1) * 4;              // this thread loads 4 consecutive k of one row of each tile
+  const int64_t am = m0 + lrow;
+  const int bn = n0 + lrow;
+  const float* ap = g.A + am * g.a_rs + lk;
+  const float* bp = g.B + (int64_t)bn * g.b_rs + lk;
+  const bool a_ok = am < g.M, b_ok = bn < g.N;
+  const int K = (int)g.K;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float ra[4], rb[4];
+  auto load_g = [&](int k0) {
+    if (kVecA && a_ok && k0 + lk + 3 < K) {
+      const float4 v = *reinterpret_cast<const float4*>(ap + k0);
+      ra[0] = v.x; ra[1] = v.y; ra[2] = v.z; ra[3] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ra[i] = (a_ok && k0 + lk + i < K) ? ap[k0 + i] : 0.f;
+    }
+    if (kVecB && b_ok && k0 + lk + 3 < K) {
+      const float4 v = *reinterpret_cast<const float4*>(bp + k0);
+      rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; rb[3] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rb[i] = (b_ok && k0 + lk + i < K) ? bp[k0 + i] : 0.f;
+    }
+  };
+  auto store_s = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { As[buf][lk + i][lrow] = ra[i]; Bs[buf][lk + i][lrow] = rb[i]; }
+  };
+  const int KT = (K + FBK - 1) / FBK;
+  load_g(0);
+  store_s(0);
+  __syncthreads();
+  for (int kt = 0; kt < KT; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < KT) load_g((kt + 1) * FBK);               // in flight while this tile is multiplied
+#pragma unroll
+    for (int kk = 0; kk < FBK; ++kk) {
+      float a[8], b[8];
+      *(float4*)&a[0] = *(const float4*)&As[buf][kk][ty * 8];
+      *(float4*)&a[4] = *(const float4*)&As[buf][kk][ty * 8 + 4];
+      *(float4*)&b[0] = *(const float4*)&Bs[buf][kk][tx * 8];
+      *(float4*)&b[4] = *(const float4*)&Bs[buf][kk][tx * 8 + 4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < KT) store_s(buf ^ 1);
+    __syncthreads();
+  }
+  // ---- epilogue: + bias, ReLU, 16-byte stores where the output pitch allows ----
+  const bool vec_c = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (n0 + BN <= g.N);
+  float bias[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const int n = n0 + tx * 8 + j; bias[j] = (g.bias != nullptr && n < g.N) ? g.bias[n] : 0.f; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ty * 8 + i;
+    if (m >= g.M) continue;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = acc[i][j] + bias[j]; if (g.relu) v[j] = fmaxf(v[j], 0.f); }
+    float* c = g.C + m * g.ldc + n0 + tx * 8;
+    if (vec_c) {
+      *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (n0 + tx * 8 + j < g.N) c[j] = v[j];
+    }
+  }
+}
+
+// Heads (sigma 256 -> 1, rgb 128 -> 3): N <= 4 outputs per row -- one warp per row, lanes split K, warp-level sum.
+// (Through the tiled SGEMM a 1-wide head cost as much as a 128-wide layer.)
+__global__ void __launch_bounds__(256) head_gemv_kernel(GemmArgs g) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  const int K = (int)g.K, N = g.N;
+  for (int64_t m = warp0; m < g.M; m += nwarps) {
+    const float* a = g.A + m * g.a_rs;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < K; k += 32) {
+      const float av = a[k];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+        if (n < N) acc[n] = fmaf(av, g.B[(int64_t)n * g.b_rs + k], acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float v = warp_sum(acc[n]);
+      if (lane == 0 && n < N) g.C[m * g.ldc + n] = v + (g.bias != nullptr ? g.bias[n] : 0.f);
+    }
+  }
+}
+
 static int run_gemm(const GemmArgs& g, cudaStream_t st) {
   if (g.M == 0 || g.N == 0) return 0;
+  const bool plain = g.a_cs == 1 && g.b_cs == 1 && !g.atomic && g.mask == nullptr && g.r1_row == nullptr && g.k_chunk >= g.K;
+  if (plain && g.N <= 4 && !g.relu) {
+    int64_t blocks = ceil_div(g.M, 8);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    head_gemv_kernel<<<(unsigned)blocks, 256, 0, st>>>(g);
+    NERF_LAUNCH_CHECK("head_gemv_kernel");
+    return 0;
+  }
+  if (plain && g.N >= 64) {
+    const bool va = ((g.a_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
+    const bool vb = ((g.b_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
+    dim3 grid(ceil_div(g.M, BM), ceil_div(g.N, BN));
+    if (va && vb) sgemm_fwd_kernel<true, true><<<grid, 256, 0, st>>>(g);
+    else if (va) sgemm_fwd_kernel<true, false><<<grid, 256, 0, st>>>(g);
+    else if (vb) sgemm_fwd_kernel<false, true><<<grid, 256, 0, st>>>(g);
+    else sgemm_fwd_kernel<false, false><<<grid, 256, 0, st>>>(g);
+    NERF_LAUNCH_CHECK("sgemm_fwd_kernel");
+    return 0;
+  }
   dim3 grid(ceil_div(g.M, BM), ceil_div(g.N, BN), g.atomic ? ceil_div(g.K, g.k_chunk) : 1);
   sgemm_kernel<<<grid, 256, 0, st>>>(g);
   NERF_LAUNCH_CHECK("sgemm_kernel");

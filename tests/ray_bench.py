@@ -12,8 +12,14 @@ import nerf_mlp_b200 as nb
 from nerf_mlp_b200 import ops
 
 
-def t(fn, iters=10):
-    for _ in range(3):
+ITERS = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+WARM = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+SIZES = tuple(int(x) for x in sys.argv[3:]) or (16384, 262144)
+
+
+def t(fn, iters=None):
+    iters = iters or ITERS
+    for _ in range(WARM):
         fn()
     torch.cuda.synchronize()
     ts = []
@@ -26,7 +32,7 @@ def t(fn, iters=10):
 
 def main():
     dev = torch.device("cuda")
-    for R in (16384, 262144):
+    for R in SIZES:
         S_c, N_imp = 64, 128
         S = S_c + N_imp
         g = torch.Generator(dev).manual_seed(0)
