@@ -38,8 +38,10 @@
 namespace nerf {
 using namespace ptx;
 
-// Measured and dropped: dedicated store warps and TMA bulk stores for the tile-image saves (both
-// slower than the per-warp coalesced copies: bulk S2G 0.34 vs 0.31 ms on the 196 608-row save pass).
+// Measured and dropped: TMA bulk stores for the tile-image saves (bulk S2G 0.34 vs 0.31 ms on the 196 608-row save
+// pass: they queue behind the same SM's bulk loads).  Dedicated LSU copy warps (below) measure equal to the epilogue
+// warps copying their own blocks (0.306 vs 0.316 / 0.245 vs 0.242 ms) and are kept because they let all eight
+// compute warps share every epilogue; NERF_TC_COPY_WARPS=0 restores the round-1 arrangement.
 constexpr int kThreads = 352;                     // producer, 2 mma issuers, 8 prologue/epilogue warps
 // Kernels that write tile images to HBM (save-mode forward, dgrad chain) get 4 more warps that do nothing but the
 // copy-out: the tile in shared memory is byte for byte its HBM image, so a copy warp moves one whole 16 KB feature
