@@ -169,6 +169,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
 // (Round 1's generic kernel reached 18.5 TFLOP/s, slower than eager PyTorch on the same GPU.)
 // ------------------------------------------------------------------------------------------
 constexpr int FBK = 8;
+// (Measured and dropped: the same loop on packed FFMA2 -- fma.rn.f32x2, two FMAs per instruction, A stored duplicated in
+// shared memory.  Issue-slot use fell from 71 % to 46 % but the FMA pipe stayed at 58-60 % busy and the layer took
+// 0.85 ms instead of 0.82: the limit of this kernel is the FMA pipe's operand delivery, not instruction issue.)
 template <bool kVecA, bool kVecB>
 __global__ void __launch_bounds__(256, 2) sgemm_fwd_kernel(GemmArgs g) {
   __shared__ __align__(16) float As[2][FBK][BM + 4];
@@ -219,11 +222,15 @@ __global__ void __launch_bounds__(256, 2) sgemm_fwd_kernel(GemmArgs g) {
     if (kt + 1 < KT) load_g((kt + 1) * FBK);               // in flight while this tile is multiplied
 #pragma unroll
     for (int kk = 0; kk < FBK; ++kk) {
+      // a thread's 8 x 8 outputs are rows {4 ty .. +3, 64 + 4 ty .. +3} x columns {4 tx .. +3, 64 + 4 tx .. +3}: the 16 tx
+      // lanes of a half-warp then read 256 contiguous bytes of Bs per LDS.128 (conflict-free; with 8 consecutive
+      // columns per thread the 32-byte stride made every B read a 2-way bank conflict and the shared-memory pipe as
+      // busy as the FMA pipe: 0.97 -> 0.82 ms per 262 144 x 256 x 256 layer)
       float a[8], b[8];
-      *(float4*)&a[0] = *(const float4*)&As[buf][kk][ty * 8];
-      *(float4*)&a[4] = *(const float4*)&As[buf][kk][ty * 8 + 4];
-      *(float4*)&b[0] = *(const float4*)&Bs[buf][kk][tx * 8];
-      *(float4*)&b[4] = *(const float4*)&Bs[buf][kk][tx * 8 + 4];
+      *(float4*)&a[0] = *(const float4*)&As[buf][kk][ty * 4];
+      *(float4*)&a[4] = *(const float4*)&As[buf][kk][64 + ty * 4];
+      *(float4*)&b[0] = *(const float4*)&Bs[buf][kk][tx * 4];
+      *(float4*)&b[4] = *(const float4*)&Bs[buf][kk][64 + tx * 4];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -234,23 +241,24 @@ __global__ void __launch_bounds__(256, 2) sgemm_fwd_kernel(GemmArgs g) {
   }
   // ---- epilogue: + bias, ReLU, 16-byte stores where the output pitch allows ----
   const bool vec_c = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (n0 + BN <= g.N);
+  auto col_of = [&](int j) { return n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4)); };
   float bias[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { const int n = n0 + tx * 8 + j; bias[j] = (g.bias != nullptr && n < g.N) ? g.bias[n] : 0.f; }
+  for (int j = 0; j < 8; ++j) { const int n = col_of(j); bias[j] = (g.bias != nullptr && n < g.N) ? g.bias[n] : 0.f; }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int64_t m = m0 + ty * 8 + i;
+    const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (m >= g.M) continue;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { v[j] = acc[i][j] + bias[j]; if (g.relu) v[j] = fmaxf(v[j], 0.f); }
-    float* c = g.C + m * g.ldc + n0 + tx * 8;
+    float* c = g.C + m * g.ldc;
     if (vec_c) {
-      *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      *reinterpret_cast<float4*>(c + col_of(0)) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(c + col_of(4)) = make_float4(v[4], v[5], v[6], v[7]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) if (n0 + tx * 8 + j < g.N) c[j] = v[j];
+      for (int j = 0; j < 8; ++j) if (col_of(j) < g.N) c[col_of(j)] = v[j];
     }
   }
 }
@@ -292,9 +300,9 @@ static int run_gemm(const GemmArgs& g, cudaStream_t st) {
     const bool va = ((g.a_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
     const bool vb = ((g.b_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
     dim3 grid(ceil_div(g.M, BM), ceil_div(g.N, BN));
+    // (the mixed variants -- one operand with 16-byte loads, the other scalar -- measured SLOWER than all-scalar:
+    // 1.04 vs ~0.85 ms per 262 144 x 256 x 256 layer, so a misaligned operand sends both down the scalar path)
     if (va && vb) sgemm_fwd_kernel<true, true><<<grid, 256, 0, st>>>(g);
-    else if (va) sgemm_fwd_kernel<true, false><<<grid, 256, 0, st>>>(g);
-    else if (vb) sgemm_fwd_kernel<false, true><<<grid, 256, 0, st>>>(g);
     else sgemm_fwd_kernel<false, false><<<grid, 256, 0, st>>>(g);
     NERF_LAUNCH_CHECK("sgemm_fwd_kernel");
     return 0;
@@ -347,7 +355,7 @@ static Fp32Bufs carve(float* ws, int64_t rows, bool bwd) {
   float* p = ws;
   b.X = p; p += rows * kXLd;
   for (int i = 0; i < 8; ++i) {
-    if (i == 4) { b.H[4] = b.X + 63; b.ldH[4] = kXLd; continue; }   // layer-4 output lives inside X319
+    if (i == 4) { b.H[4] = b.X + 63; b.ldH[4] = kXLd; continue; }   // layer-4 output lives inside X (columns 63..318)
     b.H[i] = p; b.ldH[i] = 256; p += rows * 256;
   }
   b.V = p; p += rows * kVLd;
