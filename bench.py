@@ -552,6 +552,15 @@ def bench_train(cx, args, rays, K, W, full=True):
             stage_acc[k_] = stage_acc.get(k_, 0.0) + v_ / K
     cx.barrier()
     rec["stage_ms"] = {k_: round(v_, 5) for k_, v_ in stage_acc.items()}
+    if cx.world > 1:
+        if getattr(train_step, "_peer", None) is not None:
+            rec["grad_exchange"] = ("one-shot all-reduce over NVLink peer memory fused into the Adam kernel "
+                                    "(nerf_adam_step_fused_peer; no NCCL call in the step)")
+        else:
+            rec["grad_exchange"] = ("NCCL all_reduce " + ("captured in the step graph" if train_step.allreduce_in_graph
+                                                          else "between two graph replays"))
+            if getattr(train_step, "peer_allreduce_error", None):
+                rec["grad_exchange_note"] = "peer-memory path unavailable: " + train_step.peer_allreduce_error
     rec["stage_ms_note"] = ("mean device time per stage over %d instrumented replays after the timed region "
                             "(CUDA event records on the launching stream between the kernels of the replayed graph)" % K)
 
@@ -759,8 +768,9 @@ def bench_render(cx, args, total, K, W):
 
 def dp_parity(cx, args):
     """Numerical check on the REAL ranks (scripts/train.py:376 global-mean semantics):
-      * k data-parallel TrainStep steps (R rays per rank, one NCCL all-reduce per step) leave bit-identical parameters
-        on every rank, and they equal k single-rank steps on the concatenated N*R-ray batch up to summation order;
+      * k data-parallel TrainStep steps (R rays per rank; gradient exchange over peer memory fused into the Adam kernel,
+        and again with NCCL's all-reduce) leave bit-identical parameters on every rank, and they equal k single-rank
+        steps on the concatenated N*R-ray batch up to summation order;
       * render_sharded over the ranks == the unsharded render, bit for bit."""
     import numpy as np
     import torch
@@ -770,13 +780,14 @@ def dp_parity(cx, args):
     batches = [synthetic_rays(R, 900 + r) for r in range(world)]
     tgts = [np.random.default_rng(950 + r).uniform(0, 1, (R, 3)).astype(np.float32) for r in range(world)]
     res = {}
-    for kind in ("dp", "single"):
+    exchange = {}
+    for kind in ("dp", "dp_nccl", "single"):
         torch.manual_seed(5)
         m = nb.NeRFMLP(precision=args.precision).to(dev)
         nb.dist.broadcast_params(m)
         p0 = m.flat_params.detach().clone()
         r_ = nb.NeRFRenderer(m, dev, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=0.0)
-        if kind == "dp":
+        if kind in ("dp", "dp_nccl"):
             opt = nb.FlatAdam(m, lr=5e-4)
             o, d, t = batches[rank][0], batches[rank][1], tgts[rank]
             n = R
@@ -784,7 +795,8 @@ def dp_parity(cx, args):
             opt = nb.FlatAdam(m, lr=5e-4, world_size=1)                    # no all-reduce: the whole batch on this rank
             o = np.concatenate([b[0] for b in batches]); d = np.concatenate([b[1] for b in batches]); t = np.concatenate(tgts)
             n = R * world
-        step = nb.TrainStep(r_, opt, n)
+        step = nb.TrainStep(r_, opt, n, peer_allreduce=(kind != "dp_nccl"))   # "dp": peer-memory exchange if available
+        exchange[kind] = "peer" if getattr(step, "_peer", None) is not None else "nccl"
         o, d, t = (torch.from_numpy(a).to(dev) for a in (o, d, t))
         losses = []
         for _ in range(k):
@@ -794,6 +806,14 @@ def dp_parity(cx, args):
         res[kind] = (m.flat_params.detach().clone(), losses, p0)
     p_dp, l_dp, p0 = res["dp"]
     p_1, l_1, _ = res["single"]
+    p_nccl = res["dp_nccl"][0]
+    # the two gradient-exchange paths differ in the order of the `world` summands (and, like any two runs, in the
+    # split-K reduction order of the weight-gradient kernels)
+    rel_paths = float((p_dp - p_nccl).norm() / (p_1 - p0).norm())
+    ref_n = p_nccl.clone()
+    td.broadcast(ref_n, src=0)
+    nccl_ranks_differ = torch.tensor([float((ref_n != p_nccl).sum())], device=dev, dtype=torch.float64)
+    td.all_reduce(nccl_ranks_differ, op=td.ReduceOp.SUM)
     # (a) identical across ranks: compare with rank 0's copy
     ref0 = p_dp.clone()
     td.broadcast(ref0, src=0)
@@ -821,11 +841,14 @@ def dp_parity(cx, args):
     render_mismatch = torch.tensor([float((full != shard).sum())], device=dev, dtype=torch.float64)
     td.all_reduce(render_mismatch, op=td.ReduceOp.SUM)
     out = {"world": world, "rays_per_rank": R, "steps": k, "perturb": 0.0,
-           "params_differ_across_ranks": int(ranks_differ), "dp_vs_single_max_abs": float(diff.max()),
+           "grad_exchange": exchange["dp"], "params_differ_across_ranks": int(ranks_differ),
+           "nccl_path_params_differ_across_ranks": int(nccl_ranks_differ), "peer_vs_nccl_rel_l2_of_update": rel_paths,
+           "dp_vs_single_max_abs": float(diff.max()),
            "dp_vs_single_frac_le_1e-6": float((diff <= 1e-6).float().mean()),
            "dp_vs_single_rel_l2_of_update": rel_update, "loss_rel_diff_max": loss_rel,
            "sharded_render_mismatching_values": int(render_mismatch),
-           "ok": bool(int(ranks_differ) == 0 and rel_update <= 2e-2 and loss_rel <= 1e-4 and int(render_mismatch) == 0),
+           "ok": bool(int(ranks_differ) == 0 and int(nccl_ranks_differ) == 0 and rel_update <= 2e-2 and rel_paths <= 2e-2
+                      and loss_rel <= 1e-4 and int(render_mismatch) == 0),
            "note": "params after 3 Adam steps; Adam's first steps are sign-like (lr*g/(|g|+eps)), so elements whose gradient is "
                    "near 0 amplify summation-order noise: the gate is on the relative L2 of the whole update, max/fraction are reported"}
     return out

@@ -171,6 +171,19 @@ int nerf_adam_step_dev(float* params, const float* grads, float* exp_avg, float*
 size_t nerf_adam_fused_scratch_bytes(int64_t n);
 int nerf_adam_step_fused(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                          double* state, const float* loss, void* scratch, void* stream);
+/* Data-parallel variant: gradient exchange + nerf_adam_step_fused in ONE kernel over NVLink peer memory (replaces
+ * torch.distributed.all_reduce(flat_grad) + the update; reference: scripts/train.py has no multi-GPU path, the
+ * data-parallel contract is SURVEY.md section 8e).  peer_grads[r] / peer_flags[r] (HOST arrays of `world` DEVICE
+ * pointers, r = 0 .. world-1, r == rank is this process) point into every rank's symmetric (peer-mapped) block:
+ * its flat fp32 gradient (n floats, 16-byte aligned) and 2 * NERF_PEER_MAX + 1 u32 flags, zeroed once by the caller
+ * before the first step (with a host barrier after the zeroing).  Every rank sums the `world` gradients in rank
+ * order, so all ranks compute bit-identical parameters; the gradient buffers keep the rank-LOCAL gradients.  The
+ * kernel returns only when no peer reads this rank's gradient any more.  `scratch` as for nerf_adam_step_fused
+ * (sized for n); state[4] (grad_scale) is 1 / world. */
+#define NERF_PEER_MAX 8
+int nerf_adam_step_fused_peer(float* params, const float* const* peer_grads, uint32_t* const* peer_flags, int rank,
+                              int world, float* exp_avg, float* exp_avg_sq, int64_t n, double* state, const float* loss,
+                              void* scratch, void* stream);
 
 /* The fine-pass compositing of a training step in ONE launch (scripts/train.py:374-382 around
  * renderer.py:106-107): nerf_composite_fwd -> rgb/depth/acc maps; loss = mean((rgb_map - target)^2) (:376) and

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("NERF_B200_LIB") or os.path.join(_HERE, "csrc", "libne
 N_PARAMS = 595844
 PREC_BF16, PREC_FP32 = 0, 1
 TRAIN_STATE_DOUBLES = 96
+PEER_MAX = 8                  # NERF_PEER_MAX (include/nerf_b200.h)
 BWD_ALL, BWD_DGRAD, BWD_WGRAD = 0, 1, 2
 FWD_DENSITY_ONLY = 2
 
@@ -47,6 +48,7 @@ SIGNATURES = {
     "nerf_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
     "nerf_adam_fused_scratch_bytes": (c_size_t, [c_int64]),
     "nerf_adam_step_fused": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P]),
+    "nerf_adam_step_fused_peer": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P]),
     "nerf_composite_train_scratch_bytes": (c_size_t, [c_int]),
     "nerf_composite_train": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "nerf_generate_rays": (c_int, [_P, c_int, c_int, c_int, c_double, _P, c_int64, c_int64, _P, _P, _P, _P, c_int, _P, _P]),

@@ -138,9 +138,175 @@ __global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ p, 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Data-parallel step, gradient exchange + Adam in ONE kernel over NVLink peer memory (no NCCL call):
+// every rank's flat gradient lives in a symmetric (peer-mapped) buffer; each rank reads all `world` gradients
+// straight out of the peers' HBM (one-shot all-reduce: ld.volatile.v4 over NVLink, all `world` loads of an element in
+// flight before the first add), sums them IN RANK ORDER -- so every rank computes bit-identical sums and
+// parameters -- and applies the update.  What NCCL's all-reduce + the separate Adam launch did in two kernels and
+// three passes over the gradient is one pass here.
+//
+// Hand-shake (u32 flags in each rank's symmetric block, epoch e = 1, 2, ... kept in the block itself so that the
+// kernel can be replayed from a CUDA graph):
+//   flags[r]          rank r's gradient of epoch >= value is complete              (written by rank r, st.release.sys)
+//   flags[kPeerMax+r] rank r has finished reading MY gradient of epoch >= value     (written by rank r)
+//   flags[2 kPeerMax] my epoch (advanced by the last block, after everything else)
+// Start: block 0 raises "my gradient is complete" at every peer; every block waits until all `world` gradients are.
+// End: the last block of the grid raises "I have read yours" at every peer and waits for theirs, so the kernel (and
+// with it the stream) does not pass until nobody reads this rank's gradient buffer any more -- the next step may
+// zero it.  Waits are bounded (~4 s) and trap.
+// ------------------------------------------------------------------------------------------
+constexpr int kPeerMax = NERF_PEER_MAX;
+struct PeerArgs {
+  const float* grads[kPeerMax];
+  uint32_t* flags[kPeerMax];
+  int rank, world;
+};
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer_v4(const float* p) {        // not cached in L1: the peer rewrites it every step
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer(const float* p) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_wait(const uint32_t* flag, uint32_t e, int what, int r) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < e) {
+    __nanosleep(40);
+    if (clock64() - t0 > (1ll << 33)) {
+      printf("nerf_b200: peer gradient exchange: wait timeout (%s of rank %d, epoch %u, have %u)\n",
+             what == 0 ? "gradient-ready flag" : "read-done flag", r, e, ld_acquire_sys(flag));
+      __trap();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_fused_peer_kernel(float* __restrict__ p, const PeerArgs pa, float* __restrict__ m,
+                                                              float* __restrict__ v, int64_t n, double* __restrict__ st,
+                                                              const float* __restrict__ loss, double* __restrict__ scratch) {
+  __shared__ float sc[7];
+  __shared__ double part[8];
+  __shared__ bool last;
+  __shared__ uint32_t s_epoch;
+  uint32_t* mine = pa.flags[pa.rank];
+  if (threadIdx.x == 0) {
+    const double lr = st[0], b1 = st[1], b2 = st[2], step = st[5] + 1.0;
+    const double bc1 = 1.0 - pow(b1, step), bc2 = 1.0 - pow(b2, step);
+    sc[0] = (float)(1.0 - b1); sc[1] = (float)b2; sc[2] = (float)(1.0 - b2);
+    sc[3] = (float)(-(lr / bc1)); sc[4] = (float)sqrt(bc2); sc[5] = (float)st[3]; sc[6] = (float)st[4];
+    s_epoch = *reinterpret_cast<volatile uint32_t*>(mine + 2 * kPeerMax) + 1u;
+  }
+  __syncthreads();
+  const uint32_t e = s_epoch;
+  if (blockIdx.x == 0 && (int)threadIdx.x < pa.world) st_release_sys(pa.flags[threadIdx.x] + pa.rank, e);
+  if ((int)threadIdx.x < pa.world) peer_wait(mine + threadIdx.x, e, 0, (int)threadIdx.x);
+  __syncthreads();
+
+  auto update = [&](float graw, float& pi, float& mi, float& vi) {
+    const float gi = graw * sc[6];
+    mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(gi, mi), sc[0]));
+    vi = __fadd_rn(__fmul_rn(vi, sc[1]), __fmul_rn(__fmul_rn(gi, gi), sc[2]));
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), sc[4]), sc[5]);
+    pi = __fadd_rn(pi, __fdiv_rn(__fmul_rn(sc[3], mi), denom));
+  };
+  double sq = 0.0;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 t[kPeerMax];
+#pragma unroll
+    for (int r = 0; r < kPeerMax; ++r)
+      if (r < pa.world) t[r] = ld_peer_v4(pa.grads[r] + 4 * i);
+    float4 g = t[0];
+#pragma unroll
+    for (int r = 1; r < kPeerMax; ++r)
+      if (r < pa.world) { g.x = __fadd_rn(g.x, t[r].x); g.y = __fadd_rn(g.y, t[r].y); g.z = __fadd_rn(g.z, t[r].z); g.w = __fadd_rn(g.w, t[r].w); }
+    sq += (double)g.x * (double)g.x + (double)g.y * (double)g.y + (double)g.z * (double)g.z + (double)g.w * (double)g.w;
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    update(g.x, pp.x, mm.x, vv.x); update(g.y, pp.y, mm.y, vv.y); update(g.z, pp.z, mm.z, vv.z); update(g.w, pp.w, mm.w, vv.w);
+    reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  if (blockIdx.x == 0 && (int64_t)threadIdx.x < n - 4 * n4) {                      // tail (n not a multiple of 4)
+    const int64_t i = 4 * n4 + threadIdx.x;
+    float g = ld_peer(pa.grads[0] + i);
+    for (int r = 1; r < pa.world; ++r) g = __fadd_rn(g, ld_peer(pa.grads[r] + i));
+    sq += (double)g * (double)g;
+    update(g, p[i], m[i], v[i]);
+  }
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += part[w];
+    scratch[1 + blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned int*>(scratch), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  // last block: every block of this rank has read the peers' gradients -> tell them, and wait until they have read ours
+  __threadfence();
+  if ((int)threadIdx.x < pa.world) {
+    st_release_sys(pa.flags[threadIdx.x] + kPeerMax + pa.rank, e);
+    peer_wait(mine + kPeerMax + threadIdx.x, e, 1, (int)threadIdx.x);
+  }
+  double ss = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) ss += *(volatile double*)(scratch + 1 + b);
+  ss = warp_sum(ss);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ss = 0.0;
+    for (int w = 0; w < 8; ++w) ss += part[w];
+    *reinterpret_cast<unsigned int*>(scratch) = 0u;
+    const double l = loss != nullptr ? (double)*loss : 0.0;
+    st[5] = st[5] + 1.0;
+    st[10] = l;
+    st[11] = l > 0.0 ? 10.0 * log10(1.0 / l) : INFINITY;
+    st[12] = sqrt(ss) * fabs(st[4]);
+    *reinterpret_cast<volatile uint32_t*>(mine + 2 * kPeerMax) = e;               // epoch done
+  }
+}
+
 }  // namespace nerf
 
 using namespace nerf;
+
+extern "C" int nerf_adam_step_fused_peer(float* params, const float* const* peer_grads, uint32_t* const* peer_flags,
+                                         int rank, int world, float* exp_avg, float* exp_avg_sq, int64_t n, double* state,
+                                         const float* loss, void* scratch, void* stream) {
+  NERF_CHECK_ARG(params && peer_grads && peer_flags && exp_avg && exp_avg_sq && state && scratch && n >= 1,
+                 "nerf_adam_step_fused_peer: bad arguments");
+  NERF_CHECK_ARG(world >= 1 && world <= kPeerMax && rank >= 0 && rank < world,
+                 "nerf_adam_step_fused_peer: rank %d / world %d (at most %d peers)", rank, world, kPeerMax);
+  NERF_CHECK_ARG((((uintptr_t)state | (uintptr_t)scratch) & 7) == 0, "nerf_adam_step_fused_peer: state/scratch must be 8-byte aligned");
+  NERF_CHECK_ARG((((uintptr_t)params | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
+                 "nerf_adam_step_fused_peer: params / moments must be 16-byte aligned");
+  PeerArgs pa{};
+  pa.rank = rank; pa.world = world;
+  for (int r = 0; r < world; ++r) {
+    NERF_CHECK_ARG(peer_grads[r] && peer_flags[r] && ((uintptr_t)peer_grads[r] & 15) == 0, "nerf_adam_step_fused_peer: peer %d pointers", r);
+    pa.grads[r] = peer_grads[r];
+    pa.flags[r] = peer_flags[r];
+  }
+  const int64_t n4 = n >> 2;
+  int blocks = (int)(ceil_div(n4 > 0 ? n4 : 1, 256) < 592 ? ceil_div(n4 > 0 ? n4 : 1, 256) : 592);
+  adam_fused_peer_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, pa, exp_avg, exp_avg_sq, n, state, loss, (double*)scratch);
+  NERF_LAUNCH_CHECK("adam_fused_peer_kernel");
+  return 0;
+}
 
 extern "C" size_t nerf_adam_fused_scratch_bytes(int64_t n) { return (size_t)(1 + ceil_div(n > 0 ? n : 1, 256)) * sizeof(double); }
 

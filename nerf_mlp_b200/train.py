@@ -49,7 +49,7 @@ class TrainStep:
     """
 
     def __init__(self, renderer, optimizer, n_rays, *, graph=True, warmup=2, stage_events=False, split_graphs=None,
-                 graph_allreduce=True):
+                 graph_allreduce=True, peer_allreduce=True):
         self.renderer, self.opt, self.model = renderer, optimizer, renderer.model
         if torch.device(renderer.device).type != "cuda":
             raise RuntimeError("nerf_mlp_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -65,6 +65,13 @@ class TrainStep:
         self.dev = renderer.device
         m = self.model
         m._ensure_flat()
+        # world_size > 1: gradient exchange + Adam as ONE kernel over NVLink peer memory (nerf_adam_step_fused_peer): the
+        # flat gradient buffer is placed in symmetric memory so that every rank can read every other rank's.  Falls
+        # back to NCCL's all-reduce (captured in the step graph) when symmetric memory cannot be set up.
+        self._peer = None
+        self.peer_allreduce_error = None
+        if peer_allreduce and self._world() > 1 and not split_graphs:
+            self._setup_peer()
         m._bind_flat_grads()
         optimizer._ensure_moments()
         f32 = dict(device=self.dev, dtype=torch.float32)
@@ -185,16 +192,67 @@ class TrainStep:
         m, opt = self.model, self.opt
         n = m.flat_params.numel()
         st = stream_ptr(self.dev)
-        if self._world() > 1:
+        if self._world() > 1 and self._peer is None:
             self._mark("grad_allreduce")
-        # metrics (loss, PSNR, grad norm) + step counter + Adam: ONE launch (nerf_adam_step_fused)
-        check(dll().nerf_adam_step_fused(ptr(m.flat_params), ptr(m._flat_grad), ptr(opt._m), ptr(opt._v), n,
-                                         ptr(self.state), ptr(self._loss), ptr(self._scratch_a), st), "nerf_adam_step_fused")
+        if self._peer is not None:
+            # gradient exchange (one-shot all-reduce over peer memory, summed in rank order) + metrics + Adam: ONE launch
+            pr = self._peer
+            check(dll().nerf_adam_step_fused_peer(ptr(m.flat_params), pr["grads"], pr["flags"], pr["rank"], pr["world"],
+                                                  ptr(opt._m), ptr(opt._v), n, ptr(self.state), ptr(self._loss),
+                                                  ptr(self._scratch_a), st), "nerf_adam_step_fused_peer")
+        else:
+            # metrics (loss, PSNR, grad norm) + step counter + Adam: ONE launch (nerf_adam_step_fused)
+            check(dll().nerf_adam_step_fused(ptr(m.flat_params), ptr(m._flat_grad), ptr(opt._m), ptr(opt._v), n,
+                                             ptr(self.state), ptr(self._loss), ptr(self._scratch_a), st), "nerf_adam_step_fused")
         if r_is_bf16(self.renderer):
             check(dll().nerf_pack_weights(ptr(m.flat_params), ptr(m._packed), st), "nerf_pack_weights")
         self._mark("metrics+adam+repack")
 
+    def _setup_peer(self):
+        """Place the flat gradient buffer in symmetric memory and exchange the peers' pointers.  On any failure the
+        step keeps NCCL's all-reduce (the reason is kept in ``peer_allreduce_error``)."""
+        import ctypes
+        m, dist = self.model, torch.distributed
+        try:
+            import torch.distributed._symmetric_memory as symm
+            world = self._world()
+            if not (dist.is_available() and dist.is_initialized()) or world > _lib.PEER_MAX:
+                raise RuntimeError("no initialised process group" if world <= _lib.PEER_MAX else f"world {world} > {_lib.PEER_MAX}")
+            group = self.opt.process_group if self.opt.process_group is not None else dist.group.WORLD
+            n = m.flat_params.numel()
+            n_pad = (n + 127) // 128 * 128
+            n_flags = 2 * _lib.PEER_MAX + 32
+            buf = symm.empty(n_pad + n_flags, dtype=torch.float32, device=self.dev)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, group)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            if len(ptrs) != world or ptrs[hdl.rank] != buf.data_ptr():
+                raise RuntimeError("symmetric memory handle does not describe this buffer")
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group)                                   # every rank's flags are zero before anybody's first step
+            arr = ctypes.c_void_p * world
+            self._peer = {"buf": buf, "hdl": hdl, "rank": int(hdl.rank), "world": world, "n": n,
+                          "grads": arr(*ptrs), "flags": arr(*[q + 4 * n_pad for q in ptrs])}
+            for prm in m._param_list:                             # re-bind the parameters' .grad views to the new buffer
+                prm.grad = None
+            m._flat_grad = buf[:n]
+        except Exception as exc:                                  # noqa: BLE001 -- any failure means "use NCCL"
+            self._peer = None
+            self.peer_allreduce_error = f"{type(exc).__name__}: {exc}"
+        # the choice must be the same on every rank (a rank on NCCL and a rank in the peer kernel would wait forever)
+        if dist.is_available() and dist.is_initialized():
+            ok = torch.tensor([1 if self._peer is not None else 0], device=self.dev, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.opt.process_group)
+            if int(ok.item()) == 0 and self._peer is not None:
+                self._peer = None
+                self.peer_allreduce_error = "another rank could not set up symmetric memory"
+                for prm in m._param_list:
+                    prm.grad = None
+                m._flat_grad = None
+
     def _allreduce(self):
+        if self._peer is not None:
+            return                                                # done inside nerf_adam_step_fused_peer
         if self._world() > 1:
             torch.distributed.all_reduce(self.model._flat_grad, op=torch.distributed.ReduceOp.SUM,
                                          group=self.opt.process_group)
@@ -220,6 +278,9 @@ class TrainStep:
         initialisation, allocator warm-up); parameters, Adam moments and the RNG state are restored
         afterwards, so constructing a TrainStep does not train."""
         m, opt = self.model, self.opt
+        if self._peer is not None and (m._flat_grad is None or m._flat_grad.data_ptr() != self._peer["buf"].data_ptr()):
+            raise RuntimeError("TrainStep: the model's flat gradient buffer was re-created after the peer-memory "
+                               "gradient exchange was set up; construct a new TrainStep (or pass peer_allreduce=False)")
         if r_is_bf16(self.renderer):
             m.packed_weights()                                        # clean packed image before capture
         opt._ensure_moments()
@@ -239,7 +300,7 @@ class TrainStep:
             multi = self._world() > 1
             split = multi if self.split_graphs is None else (self.split_graphs or multi)
             self.allreduce_in_graph = False
-            if multi and self.graph_allreduce and not self.split_graphs:
+            if multi and (self.graph_allreduce or self._peer is not None) and not self.split_graphs:
                 try:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):

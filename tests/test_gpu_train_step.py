@@ -281,3 +281,64 @@ def test_pipelined_submit_result(nb):
     step = nb.TrainStep(r, opt, R)
     tk = step.submit(*(b.to(DEV) for b in batches[0]))
     assert step.result(tk)["loss"] == res["blocking"][0][0]
+
+
+def test_peer_gradient_exchange_kernel_two_ranks_on_one_gpu(nb):
+    """nerf_adam_step_fused_peer (gradient exchange over peer memory + Adam in one kernel): two emulated ranks on ONE
+    GPU -- their kernels run concurrently on two streams and hand-shake through the flag words exactly as two
+    processes do over NVLink -- must both produce, bit for bit, what nerf_adam_step_fused produces on the summed
+    gradient with grad_scale = 1/2; three steps, so that the epoch counter and the "read done" hand-shake are
+    exercised.  world = 1 degenerates to nerf_adam_step_fused itself.  (Real ranks: tests/test_gpu_multi.py.)"""
+    import ctypes
+    from nerf_mlp_b200 import _lib
+    dll, ptr = _lib.dll(), _lib.ptr
+    n = 10_003                                                   # not a multiple of 4: the scalar tail is exercised
+    n_pad = (n + 127) // 128 * 128
+    n_flags = 2 * _lib.PEER_MAX + 32
+    g = torch.Generator(DEV).manual_seed(3)
+    f32 = dict(device=DEV, dtype=torch.float32)
+
+    def state(world):
+        s = torch.zeros(_lib.TRAIN_STATE_DOUBLES, device=DEV, dtype=torch.float64)
+        s[:6] = torch.tensor([5e-4, 0.9, 0.999, 1e-8, 1.0 / world, 0.0], dtype=torch.float64)
+        return s
+
+    def scratch():
+        return torch.zeros(int(dll.nerf_adam_fused_scratch_bytes(n)) // 8, device=DEV, dtype=torch.float64)
+
+    for world in (1, 2):
+        p_init = torch.randn(n, generator=g, **f32)
+        bufs = [torch.zeros(n_pad + n_flags, **f32) for _ in range(world)]
+        arr = ctypes.c_void_p * world
+        grads_arr = arr(*[b.data_ptr() for b in bufs])
+        flags_arr = arr(*[b.data_ptr() + 4 * n_pad for b in bufs])
+        ranks = [dict(p=p_init.clone(), m=torch.zeros(n, **f32), v=torch.zeros(n, **f32), st=state(world), sc=scratch(),
+                      stream=torch.cuda.Stream()) for _ in range(world)]
+        ref = dict(p=p_init.clone(), m=torch.zeros(n, **f32), v=torch.zeros(n, **f32), st=state(world), sc=scratch())
+        loss = torch.tensor(0.25, **f32)
+        for step in range(3):
+            local = [torch.randn(n, generator=g, **f32) * 1e-2 for _ in range(world)]
+            for b, lg in zip(bufs, local):
+                b[:n].copy_(lg)
+            total = local[0].clone()
+            for lg in local[1:]:
+                total = total + lg                                # rank order, fp32: what the kernel computes
+            torch.cuda.synchronize()
+            for r, rk in enumerate(ranks):
+                with torch.cuda.stream(rk["stream"]):
+                    _lib.check(dll.nerf_adam_step_fused_peer(ptr(rk["p"]), grads_arr, flags_arr, r, world, ptr(rk["m"]), ptr(rk["v"]),
+                                                             n, ptr(rk["st"]), ptr(loss), ptr(rk["sc"]),
+                                                             ctypes.c_void_p(rk["stream"].cuda_stream)), "peer")
+            _lib.check(dll.nerf_adam_step_fused(ptr(ref["p"]), ptr(total), ptr(ref["m"]), ptr(ref["v"]), n, ptr(ref["st"]),
+                                                ptr(loss), ptr(ref["sc"]), _lib.stream_ptr(DEV)), "fused")
+            torch.cuda.synchronize()
+            for rk in ranks:
+                for k in ("p", "m", "v"):
+                    assert torch.equal(rk[k], ref[k]), (world, step, k)
+                assert torch.equal(rk["st"][:12], ref["st"][:12]), (world, step)     # scalars, step counter, loss, psnr
+                # grad norm: fp64 sum of squares, partial sums grouped per float4 here and per element there
+                assert abs(float(rk["st"][12]) - float(ref["st"][12])) <= 1e-12 * float(ref["st"][12])
+            for b, lg in zip(bufs, local):
+                assert torch.equal(b[:n], lg)                     # the gradient buffers keep the rank-local gradients
+                flags = b[n_pad:].view(torch.int32)
+                assert int(flags[2 * _lib.PEER_MAX]) == step + 1  # epoch
