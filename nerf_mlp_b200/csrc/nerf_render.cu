@@ -347,7 +347,7 @@ __device__ __forceinline__ void composite_bwd_regs(const RayRegs<NB>& st, int r,
 }
 
 template <int NB>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)      // 64 registers at NB = 6: 4 blocks per SM; forcing 6 spills and is slower
 composite_fwd_regs_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
                           const float* __restrict__ rays_d, const float* __restrict__ noise, int R, int S,
                           int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ depth_map,
@@ -365,7 +365,9 @@ composite_fwd_regs_kernel(const float4* __restrict__ raw, const float* __restric
 }
 
 template <int NB>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// 4 resident blocks per SM (<= 64 registers, ~60 B of spill at NB = 6): the kernel is bound by latency, not by its
+// register-resident working set -- 648 us at 2 blocks per SM (98 registers), 524 at 3, 490 at 4 for 262 144 x 192
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, NB <= 6 ? 4 : 2)
 composite_bwd_regs_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
                           const float* __restrict__ rays_d, const float* __restrict__ noise, int R, int S,
                           int white_bkgd, const float* __restrict__ d_rgb, const float* __restrict__ d_depth,

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ p, 
 // Start: block 0 raises "my gradient is complete" at every peer; every block waits until all `world` gradients are.
 // End: the last block of the grid raises "I have read yours" at every peer and waits for theirs, so the kernel (and
 // with it the stream) does not pass until nobody reads this rank's gradient buffer any more -- the next step may
-// zero it.  Waits are bounded (~4 s) and trap.
+// zero it.  Waits are bounded (~18 s) and trap.
 // ------------------------------------------------------------------------------------------
 constexpr int kPeerMax = NERF_PEER_MAX;
 struct PeerArgs {
@@ -184,7 +184,7 @@ __device__ __forceinline__ void peer_wait(const uint32_t* flag, uint32_t e, int 
   const long long t0 = clock64();
   while (ld_acquire_sys(flag) < e) {
     __nanosleep(40);
-    if (clock64() - t0 > (1ll << 33)) {
+    if (clock64() - t0 > (1ll << 35)) {                  // ~18 s: ranks may be seconds apart in their first (lazy-init) step
       printf("nerf_b200: peer gradient exchange: wait timeout (%s of rank %d, epoch %u, have %u)\n",
              what == 0 ? "gradient-ready flag" : "read-done flag", r, e, ld_acquire_sys(flag));
       __trap();
