@@ -461,6 +461,9 @@ struct PdfArgs {
   const float* u; int u_shared;
   int R, NB, N_imp, S_c;
   float* samples; int64_t* inds; float* cdf_out; float* z_fine;
+  // shared-memory layout per warp, in floats (launch_pdf): cdf[lay_a] | bins[lay_a] | samples[lay_p] | coarse depths[lay_z],
+  // sized for THIS launch's NB / N_imp / S_c (the maxima would cap the kernel at 7 blocks per SM)
+  int lay_a, lay_p, lay_z;
 };
 
 // Bitonic sort of 32 * EPL values held in registers (value i of the sequence = element i % EPL of lane i / EPL):
@@ -515,10 +518,10 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(PdfArgs a) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * kPdfWarps + warp;
-  const int per_warp = 2 * kMaxBins + (kMerge ? kMaxSort : 0);
+  const int per_warp = 2 * a.lay_a + (kMerge ? a.lay_p + a.lay_z : 0);
   float* cdf = smem + (size_t)warp * per_warp;
-  float* bins = cdf + kMaxBins;
-  float* sortbuf = bins + kMaxBins;
+  float* bins = cdf + a.lay_a;
+  float* sortbuf = bins + a.lay_a;
   if (r >= a.R) return;
   const int NB = a.NB, NW = a.NB - 1;
   // bins
@@ -573,9 +576,9 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(PdfArgs a) {
     // construction (renderer.py:52-61); if a caller passes unsorted ones everything is sorted instead.
     const int n = a.S_c + a.N_imp;
     const float* z = a.z_coarse + (int64_t)r * a.S_c;
-    float* zc = sortbuf + kMaxBins;                  // coarse depths  [S_c]
-    float* merged = cdf;                             // cdf | bins are dead now: [2 * kMaxBins] >= n
-    bool sorted_in = a.N_imp <= kMaxBins;            // (the sample region of sortbuf must not reach zc)
+    float* zc = sortbuf + a.lay_p;                   // coarse depths  [S_c]
+    float* merged = cdf;                             // cdf | bins are dead now: [2 * lay_a] >= pow2(n)
+    bool sorted_in = true;
     for (int k = lane; k + 1 < a.S_c; k += 32)
       if (z[k + 1] < z[k]) sorted_in = false;
     sorted_in = __all_sync(0xffffffffu, sorted_in);
@@ -770,15 +773,26 @@ extern "C" int nerf_composite_train(const float* raw, const float* z_vals, const
   return 0;
 }
 
-static int launch_pdf(const PdfArgs& a, bool merge, cudaStream_t st) {
-  const size_t smem = (size_t)kPdfWarps * (2 * kMaxBins + (merge ? kMaxSort : 0)) * sizeof(float);
+static int launch_pdf(const PdfArgs& a_in, bool merge, cudaStream_t st) {
+  PdfArgs a = a_in;
+  auto pad32 = [](int x) { return (x + 31) / 32 * 32; };
+  auto pow2_64 = [](int x) { int p = 64; while (p < x) p <<= 1; return p; };
+  // cdf | bins hold NB floats each and, once dead, the merged depths (padded to a power of two on the fall-back sort);
+  // the sample region is sorted in place in blocks of 32 * EPL (or a power of two)
+  a.lay_a = pad32(a.NB);
+  if (merge && 2 * a.lay_a < pow2_64(a.S_c + a.N_imp)) a.lay_a = pow2_64(a.S_c + a.N_imp) / 2;
+  a.lay_p = merge ? pow2_64(a.N_imp) : 0;
+  a.lay_z = merge ? pad32(a.S_c) : 0;
+  const size_t smem = (size_t)kPdfWarps * (2 * a.lay_a + a.lay_p + a.lay_z) * sizeof(float);
+  const size_t smem_max = (size_t)kPdfWarps * (2 * kMaxBins + kMaxSort + kMaxBins) * sizeof(float);
+  NERF_CHECK_ARG(smem <= smem_max, "sample_pdf: %d bins / %d samples exceed the shared-memory layout", a.NB, a.N_imp);
   static DeviceOnce attr_set;                       // per device (function attributes are per context)
   if (merge) {
     DeviceProps dp;
     int rc = current_device(&dp);
     if (rc) return rc;
     if (attr_set.needed(dp.ordinal)) {
-      NERF_CUDA(cudaFuncSetAttribute(sample_pdf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      NERF_CUDA(cudaFuncSetAttribute(sample_pdf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
       attr_set.mark(dp.ordinal);
     }
     sample_pdf_kernel<true><<<ceil_div(a.R, kPdfWarps), kPdfWarps * 32, smem, st>>>(a);
