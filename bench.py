@@ -8,14 +8,15 @@ ONE JSON line on stdout (rank 0).  The default line carries BOTH halves of the m
 
   headline   BASELINE.json configs[1]: one training step on a 1024-ray batch per GPU (render coarse+fine -> MSE ->
              analytic backward -> Adam), bf16 tensor-core mode, synthetic rays, random-init 8x256 NeRF.  N > 1
-             (torchrun, one rank per GPU) is data-parallel with ONE flat gradient all-reduce per step (weak scaling).
+             (torchrun, one rank per GPU) is data-parallel with ONE flat-gradient exchange per step, fused with Adam into one
+             kernel over NVLink peer memory (`grad_exchange` says which path ran; NCCL is the fall-back) (weak scaling).
              `value` = whole-job rays/s with the batch resident in HBM; `e2e` = the same step through the public API
              (TrainStep.submit/result) with the batch copied from pinned host memory and the metrics read back every step.
   `render`   BASELINE.json configs[2]: the 800x800 (640 000-ray) render, rays sharded over the N ranks (strong
              scaling), same keys (value, ms_per_step, e2e, roofline, clocks).
   `train_4096` (N > 1, or --with-4096)  BASELINE.json configs[3]: 4096 rays per GPU, data-parallel.
   `dp_parity`  (N > 1)  numerical check on the real ranks: k data-parallel steps == k single-rank steps on the
-             concatenated batch; sharded render == unsharded render bit for bit.
+             concatenated batch (peer-memory exchange and NCCL); sharded render == unsharded render bit for bit.
 
 `roofline` is the TENSOR roofline of the dominant kernel of the step (SURVEY.md section 8d bounds every MLP kernel by
 the tensor cores): algorithmic FLOP per launch / CUDA-event time of that kernel inside the replayed step / the measured
