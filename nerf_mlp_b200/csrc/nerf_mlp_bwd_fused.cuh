@@ -489,25 +489,29 @@ __global__ void __launch_bounds__(kFzThreads, 1) bwd_fused_kernel(const __grid_c
       w_b = clock64() - t_dgrad_done;
       tc_fence_after();
       if (job.out_rows[rank] > 0) {
+        // Each thread holds one dW ROW (TMEM lane) x 32 columns; reduced straight from there a warp-wide RED touches 32
+        // different rows (32 separate L2 atomics, and scalar ones wherever a row of the flat gradient is not 16-byte
+        // aligned: layer 5's [x, h] split, ld = 63 / 283 / 319, bottleneck_linear behind the 257-float sigma head --
+        // those jobs' flush took ~100 k clk and set the kernel's duration).  So every 32 x 32 block is transposed
+        // through shared memory (the dgrad weight ring, idle by now: every MMA that read it has completed) and reduced
+        // row by row with lane = column: one coalesced 128-byte reduction per instruction, whatever the alignment.
         const int ncol_half = 64 * job.b_nfb;            // D columns handled by this warp: [h * ncol_half, (h + 1) * ncol_half)
-        float* orow = job.out + (int64_t)(job.out_row0[rank] + m) * job.ld_out;
-        const bool vec = ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) && (job.ncols & 3) == 0;
+        float* tile = reinterpret_cast<float*>(smem + L::kOffRing) + (warp - 4) * (32 * 33);
+        float* obase = job.out + (int64_t)(job.out_row0[rank] + q * 32) * job.ld_out;
         for (int c0 = h * ncol_half; c0 < (h + 1) * ncol_half; c0 += 32) {
           if (c0 >= job.ncols) break;
           uint32_t r[32];
           tmem_ld32(taddr + 256 + c0, r);
           tmem_ld_wait();
-          if (vec) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (c0 + j < job.ncols)
-                red_add_v4f(orow + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                            __uint_as_float(r[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < job.ncols) atomicAdd(orow + c0 + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          if (c0 + lane < job.ncols) {
+            float* ocol = obase + c0 + lane;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) atomicAdd(ocol + (int64_t)rr * job.ld_out, tile[rr * 33 + lane]);
           }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -630,10 +634,14 @@ static int launch_bwd_fused(const TcArgs& ta, void* ws, const WsLayout& L, float
   const uint8_t* xenc = b + L.xenc;
   const uint8_t* de16 = b + L.de16;
   const uint8_t* dhv = b + L.dhv;
-  static const double kSmall = [] { const char* e = getenv("NERF_FZ_SMALL"); return e ? atoi(e) / 100.0 : 0.85; }();
-  constexpr double kBig = 1.0;            // a small job re-reads dY for a 64-wide X: per chunk it is latency-bound like a big one
-  add(DPRE(0), 65536, true, xenc, 16384, 1, 0, 0, 63, true, 0, kSmall);                      // layer 0: X = x_enc
-  for (int l = 1; l <= 7; ++l) add(DPRE(l), 65536, true, ACT(l - 1), 65536, 2, l, l == 5 ? 63 : 0, 256, true, l, kBig);
+  // job weights (SM pairs are apportioned in proportion): measured finish times x pairs of each job, 1024 rays x 192
+  // (profiles/r02_fused_role_timings.txt).  A small job re-reads dY for a 64-wide X, so it costs most of a big one;
+  // layer 0's dY is the last tensor of every unit's chain, so its roles start (and end) last.
+  auto envw = [](const char* name, double dflt) { const char* e = getenv(name); return e ? atoi(e) / 100.0 : dflt; };
+  static const double kSmall = envw("NERF_FZ_SMALL", 0.85), kW0 = envw("NERF_FZ_W0", 0.85), kW5 = envw("NERF_FZ_W5", 1.0);
+  constexpr double kBig = 1.0;
+  add(DPRE(0), 65536, true, xenc, 16384, 1, 0, 0, 63, true, 0, kW0);                         // layer 0: X = x_enc
+  for (int l = 1; l <= 7; ++l) add(DPRE(l), 65536, true, ACT(l - 1), 65536, 2, l, l == 5 ? 63 : 0, 256, true, l, l == 5 ? kW5 : kBig);
   add(DPRE(5), 65536, true, xenc, 16384, 1, 5, 0, 63, false, 5, kSmall);                     // layer 5, x part of [x,h]
   add(DPRE(8), 65536, true, ACT(7), 65536, 2, L_BOTT, 0, 256, true, 8, kBig);                // bottleneck_linear
   add(dhv, 32768, false, ACT(8), 65536, 2, L_VIEW, 0, 256, true, 9, kBig);                   // view_linear: bottleneck columns + bias
