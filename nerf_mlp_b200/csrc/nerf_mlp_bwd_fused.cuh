@@ -69,6 +69,7 @@ struct FzJob {
   int out_row0[2], out_rows[2];         // first output feature of rank r's 128 TMEM lanes; rows it reduces (128, or 0 = padding half)
   int kind, need;                       // flag row of the dY tensor; publishing warps per tile
   int first_pair, npairs;
+  int single_reader;                    // this job is the only reader of its dY tensor (its chunks may be discarded from L2 after use)
 };
 struct FzArgs {
   TcArgs t;
@@ -81,8 +82,11 @@ struct FzArgs {
   int db_off[kFzKinds];                 // offset of the bias gradient fed by published tensor `kind`
   uint32_t* unit_ctr;                   // next dgrad unit (tile pair) to hand out; zeroed with the flags
   int stagger_clk;                      // start offset between consecutive pairs' first units (clocks)
+  uint32_t* progress;                   // [pairs]: unit index the pair's wgrad role has reached (0x7fffffff when done)
+  int window;                           // dgrad units may start at most this far ahead of the slowest wgrad role (0 = unthrottled)
+  int discard;                          // 1: single-reader dY chunks are dropped from L2 after their wgrad MMAs (no write-back)
 };
-__device__ long long g_fz_t[148][12];
+__device__ long long g_fz_t[148][13];
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(kFzThreads, 1) bwd_fused_kernel(const __grid_c
   const int wg_units = (!(fa.dbg & 2) && slab < job.npairs && slab < all_units) ? (all_units - 1 - slab) / job.npairs + 1 : 0;
   const long long t_begin = clock64();
   long long w_a = 0, w_b = 0;                                // development counters (per role: two kinds of waiting)
+  long long w_thr = 0;                                       // leader's producer: time units were held back by the throttle
   const int wg_chunks = wg_units * 4;                        // 64-row chunks: two per tile
 
   if (warp == 0 && lane == 0) {
@@ -184,14 +189,17 @@ __global__ void __launch_bounds__(kFzThreads, 1) bwd_fused_kernel(const __grid_c
     mbar_wait_cluster(bar_unit(k), (uint32_t)(k >> 1) & 1u, 970);
     return unit_box[k & 1];
   };
-  auto unit_post = [&](int k) {                              // leader, warp 0, lane 0
-    if (kWgOnly) return;
+  auto unit_draw = [&](int k) -> int {                       // leader, warp 0, lane 0: next unit of the global sequence
+    if (kWgOnly) return -1;
     if (k == 0 && fa.stagger_clk > 0) {
       const long long wait_clk = (long long)pair * fa.stagger_clk;
       while (clock64() - t_begin < wait_clk) __nanosleep(256);
     }
-    int u = (int)atomicAdd(fa.unit_ctr, 1u);
-    if (u >= num_units) u = -1;
+    const int u = (int)atomicAdd(fa.unit_ctr, 1u);
+    return u >= num_units ? -1 : u;
+  };
+  auto unit_post = [&](int k, int u) {                       // leader, warp 0, lane 0: hand unit u to both CTAs
+    if (kWgOnly) return;
     unit_box[k & 1] = u;
     const uint32_t rbox = mapa(sbase + L::kOffUnit + 4u * (k & 1), 1);
     asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(rbox), "r"(u) : "memory");
@@ -201,12 +209,46 @@ __global__ void __launch_bounds__(kFzThreads, 1) bwd_fused_kernel(const __grid_c
 
   if (warp < 4) {
     if (warp == 0) {
-      // ================= dgrad weight producer =================
-      if (lane == 0) {
-        uint32_t g = 0;
-        for (int k = 0;; ++k) {
-          if (rank == 0) unit_post(k);
-          if (unit_get(k) < 0) break;
+      // ================= dgrad weight producer (+ unit hand-out and throttle at the leader) =================
+      // Throttle: the dgrad chains outrun the wgrad roles (they would be done at ~80 % of the kernel), and dY that is
+      // not consumed soon leaves L2 and is re-read from HBM.  The leader therefore starts a unit only when the slowest
+      // wgrad role is within `window` units of it.  The whole warp polls the roles' progress words (one L2 round
+      // trip per poll).  No deadlock: units are handed out in increasing order and a unit, once started, never waits
+      // for a wgrad role, so every unit below (slowest + window) gets published.
+      uint32_t g = 0;
+      int prog_min = 0;                                        // last known minimum of the roles' progress (monotone)
+      for (int k = 0;; ++k) {
+        if (rank == 0) {
+          int u = 0;
+          if (lane == 0) u = unit_draw(k);
+          u = __shfl_sync(0xffffffffu, u, 0);
+          if (u >= 0 && fa.window > 0 && u > prog_min + fa.window) {
+            const long long t0 = clock64();
+            for (;;) {
+              uint32_t mn = 0x3fffffffu;
+              for (int i = lane; i < npairs; i += 32) {
+                const uint32_t v = *reinterpret_cast<volatile const uint32_t*>(fa.progress + i);
+                mn = v < mn ? v : mn;
+              }
+              mn = __reduce_min_sync(0xffffffffu, mn);
+              prog_min = (int)mn;
+              if (u <= prog_min + fa.window) break;
+              __nanosleep(200);
+              if (clock64() - t0 > (1ll << 32)) {
+                if (lane == 0) printf("nerf_b200: fused backward: throttle wait timeout block=%d unit=%d slowest=%d\n", (int)blockIdx.x, u, prog_min);
+                __trap();
+              }
+            }
+            w_thr += clock64() - t0;
+          }
+          if (lane == 0) unit_post(k, u);
+        }
+        __syncwarp();
+        int unit = 0;
+        if (lane == 0) unit = unit_get(k);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit < 0) break;
+        if (lane == 0) {
           for (int i = 0; i < nslots; ++i, ++g) {
             const uint32_t s = g % kFzRing, ph = (g / kFzRing) & 1;
             const uint2 rec = *reinterpret_cast<const uint2*>(&c_slots[slot0 + i]);      // goff, bytes
@@ -216,6 +258,7 @@ __global__ void __launch_bounds__(kFzThreads, 1) bwd_fused_kernel(const __grid_c
             bulk_g2s(sbase + L::kOffRing + s * kFzSlotK, a.packed + rec.x + rank * bytes, bytes, bar_full(s));
           }
         }
+        __syncwarp();
       }
     } else if (warp == 1) {
       if (rank != 0) {
@@ -309,6 +352,8 @@ __global__ void __launch_bounds__(kFzThreads, 1) bwd_fused_kernel(const __grid_c
           }
         }
         if (lane == 0) {
+          if (rank == 0 && (c & 3) == 0)                    // progress of this role, read by the leaders' unit throttle
+            *reinterpret_cast<volatile uint32_t*>(fa.progress + pair) = (uint32_t)(slab + (c >> 2) * job.npairs);
           if (c >= L::kStages) { const long long t_ = clock64(); mbar_wait(bar_wempty(s), ((c / L::kStages) - 1) & 1, 600 + s); w_a += clock64() - t_; }
           const int64_t tile = tile_of(ti);
           const uint32_t half = (uint32_t)(c & 1) * 8192u;          // rows 0-63 / 64-127 of the tile
@@ -325,7 +370,20 @@ __global__ void __launch_bounds__(kFzThreads, 1) bwd_fused_kernel(const __grid_c
           }
         }
         __syncwarp();
+        // The MMAs of chunk c - kStages have completed (lane 0 waited for its stage above): its dY rows are dead if
+        // this job is their only reader.  Dropping the lines from L2 spares the write-back of dY to HBM.
+        if (fa.discard && job.single_reader && c >= L::kStages) {
+          const int cd = c - L::kStages;
+          const uint8_t* d_src = job.A + tile_of(cd >> 1) * job.a_tile_bytes + (uint32_t)(cd & 1) * 8192u + lane * 128;
+#pragma unroll
+          for (int fb = 0; fb < 2; ++fb) {
+            const uint8_t* q = d_src + (a_fb + fb) * 16384;
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(q) : "memory");
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(q + 4096) : "memory");
+          }
+        }
       }
+      if (lane == 0 && rank == 0) *reinterpret_cast<volatile uint32_t*>(fa.progress + pair) = 0x7fffffffu;
     } else {
       if (rank != 0) {
         // peer: relay "my halves of stage s landed"
@@ -581,6 +639,7 @@ __global__ void __launch_bounds__(kFzThreads, 1) bwd_fused_kernel(const __grid_c
   if ((fa.dbg & 4) && lane == 0 && blockIdx.x < 148) {
     const long long t_end = clock64() - t_begin;
     long long* o = g_fz_t[blockIdx.x];
+    if (warp == 0) { o[12] = w_thr; }                        // leader's producer: throttle waits
     if (warp == 1) { o[0] = w_a; o[1] = w_b; }               // dgrad issuer: weight-slot waits, activation waits
     if (warp == 2) { o[2] = w_a; o[3] = w_b; }               // wgrad loader: stage-free waits, flag waits
     if (warp == 3) { o[4] = w_a; }                           // wgrad issuer: stage-full waits
@@ -629,6 +688,7 @@ static int launch_bwd_fused(const TcArgs& ta, void* ws, const WsLayout& L, float
     j.out_row0[0] = 0; j.out_row0[1] = full ? 128 : 0;
     j.out_rows[0] = 128; j.out_rows[1] = full ? 128 : 0;
     j.kind = kind; j.need = kFzCopyWarps;
+    j.single_reader = (kind != 5 && kind != 9) ? 1 : 0;
     weight[nj++] = w;
   };
   const uint8_t* xenc = b + L.xenc;
@@ -674,10 +734,15 @@ static int launch_bwd_fused(const TcArgs& ta, void* ws, const WsLayout& L, float
   fa.db_off[9] = (int)b_off(L_VIEW);
   fa.stagger_clk = stagger;
   fa.unit_ctr = fa.flags + (size_t)kFzKinds * ntiles;
+  fa.progress = fa.unit_ctr + 32;
+  static const int window = [] { const char* e = getenv("NERF_FZ_WINDOW"); return e ? atoi(e) : 88; }();      // sweep: profiles/r02_fused_throttle_sweep.txt
+  static const int discard = [] { const char* e = getenv("NERF_FZ_DISCARD"); return e ? atoi(e) : 1; }();
+  fa.window = window;
+  fa.discard = discard;
 
   if (!kWgOnly) {
     NERF_CUDA(cudaMemsetAsync(fa.flags, (dbg & 1) ? 0xFF : 0, (size_t)kFzKinds * ntiles * sizeof(uint32_t), st));
-    NERF_CUDA(cudaMemsetAsync(fa.unit_ctr, 0, 32 * sizeof(uint32_t), st));
+    NERF_CUDA(cudaMemsetAsync(fa.unit_ctr, 0, 160 * sizeof(uint32_t), st));
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * npairs));
@@ -694,7 +759,7 @@ static int launch_bwd_fused(const TcArgs& ta, void* ws, const WsLayout& L, float
   if (dbg & 4) {                                          // development: role timings of a few CTAs (synchronises!)
     static int printed = 0;
     if (printed++ == 3) {
-      long long h[148][12];
+      long long h[148][13];
       NERF_CUDA(cudaStreamSynchronize(st));
       NERF_CUDA(cudaMemcpyFromSymbol(h, g_fz_t, sizeof(h)));
       long long tmin = 1ll << 60, tmax = 0; int bmax = 0;
@@ -704,9 +769,9 @@ static int launch_bwd_fused(const TcArgs& ta, void* ws, const WsLayout& L, float
         const int blk = 2 * fa.jobs[j].first_pair;
         fprintf(stderr, "FZ job %2d kind %d npairs %d (CTA %3d): total %7lld clk | dgrad issuer: wait weights %7lld, wait act %7lld | "
                 "wgrad loader: wait stage %7lld, wait flag %7lld | wgrad issuer: wait full %7lld | epilogue: wait acc %7lld, tail wait dW %7lld | "
-                "epilogue phases: copy-free wait %lld, tmem->smem %lld, fence+arrive %lld, copy request %lld\n",
+                "epilogue phases: copy-free wait %lld, tmem->smem %lld, fence+arrive %lld, copy request %lld | throttle %lld\n",
                 j, fa.jobs[j].kind, fa.jobs[j].npairs, blk, h[blk][7], h[blk][0], h[blk][1], h[blk][2], h[blk][3], h[blk][4], h[blk][5], h[blk][6],
-                h[blk][8], h[blk][9], h[blk][10], h[blk][11]);
+                h[blk][8], h[blk][9], h[blk][10], h[blk][11], h[blk][12]);
       }
     }
   }

@@ -93,7 +93,7 @@ inline WsLayout ws_layout(int64_t M, int save) {
     w.hvmask = take((size_t)M * 4 * 4);
     w.dpre = take((size_t)9 * w.Mp * 256 * 2);
     w.dhv = take((size_t)w.Mp * 128 * 2);
-    w.flags = take(((size_t)10 * (w.Mp / kTileM) + 32) * 4);   // fused backward: publish counters [10 tensors][tiles] + unit counter
+    w.flags = take(((size_t)10 * (w.Mp / kTileM) + 160) * 4);  // fused backward: publish counters [10 tensors][tiles] + unit counter (32 words) + wgrad progress per SM pair (128 words)
   }
   w.total = o;
   return w;

@@ -201,7 +201,7 @@ def bf16_workspace_views(ws, M):
             ("hvmask", M * 4 * 4, torch.int32, (M, 4), None),
             ("dpre", 9 * Mp * 256 * 2, torch.bfloat16, None, (9, 256)),
             ("dhv", Mp * 128 * 2, torch.bfloat16, None, (1, 128)),
-            ("flags", (10 * (Mp // 128) + 32) * 4, torch.int32, (10 * (Mp // 128) + 32,), None))
+            ("flags", (10 * (Mp // 128) + 160) * 4, torch.int32, (10 * (Mp // 128) + 160,), None))
     for name, nbytes, dt, shape, img in spec:
         flat = ws[off:off + nbytes].view(dt)
         if img is None:
