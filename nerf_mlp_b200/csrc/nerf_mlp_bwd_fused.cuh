@@ -735,7 +735,10 @@ static int launch_bwd_fused(const TcArgs& ta, void* ws, const WsLayout& L, float
   fa.stagger_clk = stagger;
   fa.unit_ctr = fa.flags + (size_t)kFzKinds * ntiles;
   fa.progress = fa.unit_ctr + 32;
-  static const int window = [] { const char* e = getenv("NERF_FZ_WINDOW"); return e ? atoi(e) : 88; }();      // sweep: profiles/r02_fused_throttle_sweep.txt
+  // default: pairs + 20 % (88 on 148 SMs; sweep: profiles/r02_fused_throttle_sweep.txt) -- `npairs` units are in flight
+  // by construction, so anything below that serialises the chains
+  static const int window_env = [] { const char* e = getenv("NERF_FZ_WINDOW"); return e ? atoi(e) : -1; }();
+  const int window = window_env >= 0 ? window_env : npairs + npairs / 5;
   static const int discard = [] { const char* e = getenv("NERF_FZ_DISCARD"); return e ? atoi(e) : 1; }();
   fa.window = window;
   fa.discard = discard;
