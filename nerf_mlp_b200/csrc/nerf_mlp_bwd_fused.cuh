@@ -26,9 +26,15 @@
 namespace nerf {
 
 constexpr int kFzThreads = 512;                   // 4 control warps, 8 epilogue warps, 2 db warps, 2 copy-out / publish warps
-constexpr int kFzRing = 4;                        // dgrad weight ring: half-slots of 8 KB per CTA
+#ifndef NERF_FZ_RING
+#define NERF_FZ_RING 8
+#endif
+#ifndef NERF_FZ_STAGES
+#define NERF_FZ_STAGES 3
+#endif
+constexpr int kFzRing = NERF_FZ_RING;             // dgrad weight ring: half-slots of 8 KB per CTA (a layer is 8 of them)
 constexpr int kFzSlotK = kSlotBytes / 2;
-constexpr int kFzStages = 4;                      // wgrad operand ring
+constexpr int kFzStages = NERF_FZ_STAGES;         // wgrad operand ring
 constexpr int kFzStageBytes = 32768;              // A: 2 feature blocks x [64 rows][128 B] (16 KB) | B: the same
 constexpr int kFzOffA = 0, kFzOffB = 16384;
 constexpr int kFzBiasWarps = 2;
@@ -84,11 +90,17 @@ struct FzArgs {
   int stagger_clk;                      // start offset between consecutive pairs' first units (clocks)
   uint32_t* progress;                   // [pairs]: unit index the pair's wgrad role has reached (0x7fffffff when done)
   int window;                           // dgrad units may start at most this far ahead of the slowest wgrad role (0 = unthrottled)
+  int prefetch;                         // L2 prefetch distance of the X operand (saved by the forward, comes from HBM), in 64-row chunks; 0 = off
   int discard;                          // 1: single-reader dY chunks are dropped from L2 after their wgrad MMAs (no write-back)
 };
 __device__ long long g_fz_t[148][13];
 
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Cross-proxy fence for GLOBAL memory: the dY tiles are written with generic-proxy stores (another SM's copy warps) and
+// read by bulk copies (async proxy).  The ordering against the writer is the ld.acquire.gpu on the publish counter; this
+// fence only has to make the async proxy see what the generic proxy has observed.  `.global` compiles to a single
+// FENCE.VIEW.ASYNC.G -- the unqualified form adds a MEMBAR.ALL.GPU (~1 000+ clk), which with the unit throttle (small
+// batches of newly published tiles, so one fence every few chunks) sat on the wgrad loaders' critical path.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -341,8 +353,8 @@ __global__ void __launch_bounds__(kFzThreads, 1) bwd_fused_kernel(const __grid_c
         // L2 prefetch kFzPrefetch chunks ahead, on the LSU path (all 32 lanes, one 128-byte line each per instruction) so
         // that it costs the TMA unit nothing: X always (it comes from HBM, no dependency), dY if already published.
         // The 3-stage ring then only has to cover the L2 latency.
-        if (kFzPrefetch > 0 && !(fa.dbg & 8) && c + kFzPrefetch < wg_chunks) {
-          const int cp = c + kFzPrefetch;
+        if (fa.prefetch > 0 && c + fa.prefetch < wg_chunks) {
+          const int cp = c + fa.prefetch;
           const int64_t ptile = tile_of(cp >> 1);
           const uint32_t phalf = (uint32_t)(cp & 1) * 8192u;
           for (int fb = 0; fb < job.b_nfb; ++fb) {
@@ -742,6 +754,8 @@ static int launch_bwd_fused(const TcArgs& ta, void* ws, const WsLayout& L, float
   static const int discard = [] { const char* e = getenv("NERF_FZ_DISCARD"); return e ? atoi(e) : 1; }();
   fa.window = window;
   fa.discard = discard;
+  static const int prefetch = [] { const char* e = getenv("NERF_FZ_PREFETCH"); return e ? atoi(e) : kFzPrefetch; }();
+  fa.prefetch = prefetch;
 
   if (!kWgOnly) {
     NERF_CUDA(cudaMemsetAsync(fa.flags, (dbg & 1) ? 0xFF : 0, (size_t)kFzKinds * ntiles * sizeof(uint32_t), st));
