@@ -42,7 +42,7 @@ python tests/tc_bench.py 16384 192 2 0 > $O/plain_fwd.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -s 2 -c 1 -f -o $O/mlp_fwd \
     python tests/tc_bench.py 16384 192 2 0 > $O/ncu_fwd.log 2>&1
 python tests/ray_bench.py 1 1 262144 > $O/plain_ray.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"composite_|sample_pdf" -s 3 -c 3 -f -o $O/ray_kernels \
+ncu --set full --clock-control none --import-source on -k regex:"composite_|sample_pdf" -s 1 -c 5 -f -o $O/ray_kernels \
     python tests/ray_bench.py 1 1 262144 > $O/ncu_ray.log 2>&1
 ls -la $O
 # multi-GPU lines: gpurun --gpus N -- bash profiles/run_multi.sh N [--with-4096]; tests/test_gpu_multi.py on >= 2 GPUs
