@@ -555,7 +555,8 @@ def bench_train(cx, args, rays, K, W, full=True):
     rec["stage_ms"] = {k_: round(v_, 5) for k_, v_ in stage_acc.items()}
     if cx.world > 1:
         if getattr(train_step, "_peer", None) is not None:
-            rec["grad_exchange"] = ("one-shot all-reduce over NVLink peer memory fused into the Adam kernel "
+            rec["grad_exchange"] = (("two-shot (reduce-scatter + all-gather)" if train_step._peer.get("two_shot") else "one-shot")
+                                    + " all-reduce over NVLink peer memory fused into the Adam kernel "
                                     "(nerf_adam_step_fused_peer; no NCCL call in the step)")
         else:
             rec["grad_exchange"] = ("NCCL all_reduce " + ("captured in the step graph" if train_step.allreduce_in_graph

@@ -179,11 +179,15 @@ int nerf_adam_step_fused(float* params, const float* grads, float* exp_avg, floa
  * before the first step (with a host barrier after the zeroing).  Every rank sums the `world` gradients in rank
  * order, so all ranks compute bit-identical parameters; the gradient buffers keep the rank-LOCAL gradients.  The
  * kernel returns only when no peer reads this rank's gradient any more.  `scratch` as for nerf_adam_step_fused
- * (sized for n); state[4] (grad_scale) is 1 / world. */
+ * (sized for n); state[4] (grad_scale) is 1 / world.
+ * peer_red == NULL: one-shot (every rank reads all `world` gradients).  peer_red[r] != NULL (n floats in every rank's
+ * symmetric block, 16-byte aligned): two-shot -- rank r reduces slice r and stores it into every rank's `red` buffer,
+ * then every rank updates from its own copy; same results on every rank, (world-1)/world x 2n floats of NVLink traffic
+ * per rank instead of (world-1) x n.  The flag block needs 2 * NERF_PEER_MAX + 2 u32 then. */
 #define NERF_PEER_MAX 8
-int nerf_adam_step_fused_peer(float* params, const float* const* peer_grads, uint32_t* const* peer_flags, int rank,
-                              int world, float* exp_avg, float* exp_avg_sq, int64_t n, double* state, const float* loss,
-                              void* scratch, void* stream);
+int nerf_adam_step_fused_peer(float* params, const float* const* peer_grads, float* const* peer_red,
+                              uint32_t* const* peer_flags, int rank, int world, float* exp_avg, float* exp_avg_sq,
+                              int64_t n, double* state, const float* loss, void* scratch, void* stream);
 
 /* The fine-pass compositing of a training step in ONE launch (scripts/train.py:374-382 around
  * renderer.py:106-107): nerf_composite_fwd -> rgb/depth/acc maps; loss = mean((rgb_map - target)^2) (:376) and

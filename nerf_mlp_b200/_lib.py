@@ -48,7 +48,7 @@ SIGNATURES = {
     "nerf_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
     "nerf_adam_fused_scratch_bytes": (c_size_t, [c_int64]),
     "nerf_adam_step_fused": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P]),
-    "nerf_adam_step_fused_peer": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P]),
+    "nerf_adam_step_fused_peer": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P]),
     "nerf_composite_train_scratch_bytes": (c_size_t, [c_int]),
     "nerf_composite_train": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "nerf_generate_rays": (c_int, [_P, c_int, c_int, c_int, c_double, _P, c_int64, c_int64, _P, _P, _P, _P, c_int, _P, _P]),

@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ p, 
 constexpr int kPeerMax = NERF_PEER_MAX;
 struct PeerArgs {
   const float* grads[kPeerMax];
+  float* red[kPeerMax];                 // two-shot only: every rank's buffer for the reduced gradient
   uint32_t* flags[kPeerMax];
   int rank, world;
 };
@@ -280,13 +281,141 @@ __global__ void __launch_bounds__(256) adam_fused_peer_kernel(float* __restrict_
   }
 }
 
+// Two-shot variant (world >= 4): reduce-scatter + all-gather over peer memory, then the update.  Rank r sums slice r of the
+// `world` gradients (in rank order) and STORES the result into every rank's `red` buffer (fire-and-forget remote
+// stores); once all slices have landed, every rank applies Adam to the whole reduced gradient out of its own HBM.
+// NVLink traffic per rank: 2 (world-1)/world x n floats instead of (world-1) x n (at 8 GPUs 4.2 MB instead of 16.7 MB);
+// parameters and moments stay replicated and bit-identical, so nothing else in the framework changes.
+// Flags: [r] gradient ready (as above); [kPeerMax + r] "rank r's slice is in your red buffer" -- which also means rank r
+// has finished reading everybody's gradient, so the one-shot kernel's closing hand-shake is not needed: a kernel that
+// has passed the slice wait may exit.  [2 kPeerMax + 1]: block counter of the scatter phase (self-resetting).
+__device__ __forceinline__ void st_peer_v4(float* p, float4 v) {
+  asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_peer(float* p, float v) { asm volatile("st.volatile.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+__global__ void __launch_bounds__(256) adam_fused_peer2_kernel(float* __restrict__ p, const PeerArgs pa, float* __restrict__ m,
+                                                               float* __restrict__ v, int64_t n, double* __restrict__ st,
+                                                               const float* __restrict__ loss, double* __restrict__ scratch) {
+  __shared__ float sc[7];
+  __shared__ double part[8];
+  __shared__ bool last;
+  __shared__ uint32_t s_epoch;
+  uint32_t* mine = pa.flags[pa.rank];
+  if (threadIdx.x == 0) {
+    const double lr = st[0], b1 = st[1], b2 = st[2], step = st[5] + 1.0;
+    const double bc1 = 1.0 - pow(b1, step), bc2 = 1.0 - pow(b2, step);
+    sc[0] = (float)(1.0 - b1); sc[1] = (float)b2; sc[2] = (float)(1.0 - b2);
+    sc[3] = (float)(-(lr / bc1)); sc[4] = (float)sqrt(bc2); sc[5] = (float)st[3]; sc[6] = (float)st[4];
+    s_epoch = *reinterpret_cast<volatile uint32_t*>(mine + 2 * kPeerMax) + 1u;
+  }
+  __syncthreads();
+  const uint32_t e = s_epoch;
+  if (blockIdx.x == 0 && (int)threadIdx.x < pa.world) st_release_sys(pa.flags[threadIdx.x] + pa.rank, e);
+  if ((int)threadIdx.x < pa.world) peer_wait(mine + threadIdx.x, e, 0, (int)threadIdx.x);
+  __syncthreads();
+
+  // ---- reduce-scatter: this rank's slice, result broadcast into every rank's `red` ----
+  const int64_t n4 = n >> 2;
+  const int64_t per = (n4 + pa.world - 1) / pa.world;
+  const int64_t lo = per * pa.rank, hi = (lo + per < n4) ? lo + per : n4;
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 t[kPeerMax];
+#pragma unroll
+    for (int r = 0; r < kPeerMax; ++r)
+      if (r < pa.world) t[r] = ld_peer_v4(pa.grads[r] + 4 * i);
+    float4 g = t[0];
+#pragma unroll
+    for (int r = 1; r < kPeerMax; ++r)
+      if (r < pa.world) { g.x = __fadd_rn(g.x, t[r].x); g.y = __fadd_rn(g.y, t[r].y); g.z = __fadd_rn(g.z, t[r].z); g.w = __fadd_rn(g.w, t[r].w); }
+#pragma unroll
+    for (int r = 0; r < kPeerMax; ++r)
+      if (r < pa.world) st_peer_v4(pa.red[r] + 4 * i, g);
+  }
+  if (pa.rank == pa.world - 1 && blockIdx.x == 0 && (int64_t)threadIdx.x < n - 4 * n4) {   // tail (n not a multiple of 4)
+    const int64_t i = 4 * n4 + threadIdx.x;
+    float g = ld_peer(pa.grads[0] + i);
+    for (int r = 1; r < pa.world; ++r) g = __fadd_rn(g, ld_peer(pa.grads[r] + i));
+    for (int r = 0; r < pa.world; ++r) st_peer(pa.red[r] + i, g);
+  }
+  __threadfence_system();                                  // this thread's remote stores are performed before the block is counted
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* ctr = mine + 2 * kPeerMax + 1;
+    last = atomicAdd(ctr, 1u) == gridDim.x - 1;
+    if (last) *reinterpret_cast<volatile uint32_t*>(ctr) = 0u;
+  }
+  __syncthreads();
+  if (last) {                                              // the whole grid of this rank has scattered its slice
+    __threadfence_system();
+    if ((int)threadIdx.x < pa.world) st_release_sys(pa.flags[threadIdx.x] + kPeerMax + pa.rank, e);
+  }
+  if ((int)threadIdx.x < pa.world) peer_wait(mine + kPeerMax + threadIdx.x, e, 1, (int)threadIdx.x);
+  __syncthreads();
+
+  // ---- the update, on the reduced gradient in this rank's own memory (same arithmetic as adam_fused_kernel) ----
+  const float* red = pa.red[pa.rank];
+  auto update = [&](float graw, float& pi, float& mi, float& vi) {
+    const float gi = graw * sc[6];
+    mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(gi, mi), sc[0]));
+    vi = __fadd_rn(__fmul_rn(vi, sc[1]), __fmul_rn(__fmul_rn(gi, gi), sc[2]));
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), sc[4]), sc[5]);
+    pi = __fadd_rn(pi, __fdiv_rn(__fmul_rn(sc[3], mi), denom));
+  };
+  double sq = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g = ld_peer_v4(red + 4 * i);               // written by remote stores: not through L1
+    sq += (double)g.x * (double)g.x + (double)g.y * (double)g.y + (double)g.z * (double)g.z + (double)g.w * (double)g.w;
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    update(g.x, pp.x, mm.x, vv.x); update(g.y, pp.y, mm.y, vv.y); update(g.z, pp.z, mm.z, vv.z); update(g.w, pp.w, mm.w, vv.w);
+    reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  if (blockIdx.x == 0 && (int64_t)threadIdx.x < n - 4 * n4) {
+    const int64_t i = 4 * n4 + threadIdx.x;
+    const float g = ld_peer(red + i);
+    sq += (double)g * (double)g;
+    update(g, p[i], m[i], v[i]);
+  }
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += part[w];
+    scratch[1 + blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned int*>(scratch), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double ss = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) ss += *(volatile double*)(scratch + 1 + b);
+  ss = warp_sum(ss);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ss = 0.0;
+    for (int w = 0; w < 8; ++w) ss += part[w];
+    *reinterpret_cast<unsigned int*>(scratch) = 0u;
+    const double l = loss != nullptr ? (double)*loss : 0.0;
+    st[5] = st[5] + 1.0;
+    st[10] = l;
+    st[11] = l > 0.0 ? 10.0 * log10(1.0 / l) : INFINITY;
+    st[12] = sqrt(ss) * fabs(st[4]);
+    *reinterpret_cast<volatile uint32_t*>(mine + 2 * kPeerMax) = e;               // epoch done
+  }
+}
+
 }  // namespace nerf
 
 using namespace nerf;
 
-extern "C" int nerf_adam_step_fused_peer(float* params, const float* const* peer_grads, uint32_t* const* peer_flags,
-                                         int rank, int world, float* exp_avg, float* exp_avg_sq, int64_t n, double* state,
-                                         const float* loss, void* scratch, void* stream) {
+extern "C" int nerf_adam_step_fused_peer(float* params, const float* const* peer_grads, float* const* peer_red,
+                                         uint32_t* const* peer_flags, int rank, int world, float* exp_avg,
+                                         float* exp_avg_sq, int64_t n, double* state, const float* loss, void* scratch,
+                                         void* stream) {
   NERF_CHECK_ARG(params && peer_grads && peer_flags && exp_avg && exp_avg_sq && state && scratch && n >= 1,
                  "nerf_adam_step_fused_peer: bad arguments");
   NERF_CHECK_ARG(world >= 1 && world <= kPeerMax && rank >= 0 && rank < world,
@@ -300,10 +429,23 @@ extern "C" int nerf_adam_step_fused_peer(float* params, const float* const* peer
     NERF_CHECK_ARG(peer_grads[r] && peer_flags[r] && ((uintptr_t)peer_grads[r] & 15) == 0, "nerf_adam_step_fused_peer: peer %d pointers", r);
     pa.grads[r] = peer_grads[r];
     pa.flags[r] = peer_flags[r];
+    if (peer_red != nullptr) {
+      NERF_CHECK_ARG(peer_red[r] && ((uintptr_t)peer_red[r] & 15) == 0, "nerf_adam_step_fused_peer: peer %d reduced-gradient buffer", r);
+      pa.red[r] = peer_red[r];
+    }
   }
   const int64_t n4 = n >> 2;
   int blocks = (int)(ceil_div(n4 > 0 ? n4 : 1, 256) < 592 ? ceil_div(n4 > 0 ? n4 : 1, 256) : 592);
-  adam_fused_peer_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, pa, exp_avg, exp_avg_sq, n, state, loss, (double*)scratch);
+  // both kernels spin on flags written by other blocks / ranks: the whole grid must be co-resident (592 blocks of 256
+  // threads are at most 4 per SM on 148 SMs; smaller devices get a smaller grid)
+  DeviceProps dp;
+  int rc = current_device(&dp);
+  if (rc) return rc;
+  if (blocks > 4 * dp.sm_count) blocks = 4 * dp.sm_count;
+  if (peer_red != nullptr)
+    adam_fused_peer2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, pa, exp_avg, exp_avg_sq, n, state, loss, (double*)scratch);
+  else
+    adam_fused_peer_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, pa, exp_avg, exp_avg_sq, n, state, loss, (double*)scratch);
   NERF_LAUNCH_CHECK("adam_fused_peer_kernel");
   return 0;
 }

@@ -23,6 +23,7 @@ Data-parallel (world_size > 1): the step is two graphs with ONE flat NCCL all-re
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -197,7 +198,7 @@ class TrainStep:
         if self._peer is not None:
             # gradient exchange (one-shot all-reduce over peer memory, summed in rank order) + metrics + Adam: ONE launch
             pr = self._peer
-            check(dll().nerf_adam_step_fused_peer(ptr(m.flat_params), pr["grads"], pr["flags"], pr["rank"], pr["world"],
+            check(dll().nerf_adam_step_fused_peer(ptr(m.flat_params), pr["grads"], pr["red"], pr["flags"], pr["rank"], pr["world"],
                                                   ptr(opt._m), ptr(opt._v), n, ptr(self.state), ptr(self._loss),
                                                   ptr(self._scratch_a), st), "nerf_adam_step_fused_peer")
         else:
@@ -222,7 +223,10 @@ class TrainStep:
             n = m.flat_params.numel()
             n_pad = (n + 127) // 128 * 128
             n_flags = 2 * _lib.PEER_MAX + 32
-            buf = symm.empty(n_pad + n_flags, dtype=torch.float32, device=self.dev)
+            # two-shot exchange (reduce-scatter + all-gather) from 4 ranks up: a second n-float region for the reduced gradient
+            env = os.environ.get("NERF_PEER_TWO_SHOT", "")
+            two_shot = (world >= 4) if env == "" else (env != "0")
+            buf = symm.empty((2 if two_shot else 1) * n_pad + n_flags, dtype=torch.float32, device=self.dev)
             buf.zero_()
             hdl = symm.rendezvous(buf, group)
             ptrs = [int(x) for x in hdl.buffer_ptrs]
@@ -231,8 +235,10 @@ class TrainStep:
             torch.cuda.synchronize(self.dev)
             dist.barrier(group)                                   # every rank's flags are zero before anybody's first step
             arr = ctypes.c_void_p * world
-            self._peer = {"buf": buf, "hdl": hdl, "rank": int(hdl.rank), "world": world, "n": n,
-                          "grads": arr(*ptrs), "flags": arr(*[q + 4 * n_pad for q in ptrs])}
+            n_data = (2 if two_shot else 1) * n_pad
+            self._peer = {"buf": buf, "hdl": hdl, "rank": int(hdl.rank), "world": world, "n": n, "two_shot": two_shot,
+                          "grads": arr(*ptrs), "red": arr(*[q + 4 * n_pad for q in ptrs]) if two_shot else None,
+                          "flags": arr(*[q + 4 * n_data for q in ptrs])}
             for prm in m._param_list:                             # re-bind the parameters' .grad views to the new buffer
                 prm.grad = None
             m._flat_grad = buf[:n]

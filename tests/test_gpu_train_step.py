@@ -288,7 +288,9 @@ def test_peer_gradient_exchange_kernel_two_ranks_on_one_gpu(nb):
     GPU -- their kernels run concurrently on two streams and hand-shake through the flag words exactly as two
     processes do over NVLink -- must both produce, bit for bit, what nerf_adam_step_fused produces on the summed
     gradient with grad_scale = 1/2; three steps, so that the epoch counter and the "read done" hand-shake are
-    exercised.  world = 1 degenerates to nerf_adam_step_fused itself.  (Real ranks: tests/test_gpu_multi.py.)"""
+    exercised.  world = 1 degenerates to nerf_adam_step_fused itself.  Both exchange schemes: one-shot (every rank reads
+    all gradients) and two-shot (reduce-scatter + all-gather through the `red` buffers; also three ranks, whose slices
+    do not divide the buffer evenly).  (Real ranks: tests/test_gpu_multi.py.)"""
     import ctypes
     from nerf_mlp_b200 import _lib
     dll, ptr = _lib.dll(), _lib.ptr
@@ -306,12 +308,13 @@ def test_peer_gradient_exchange_kernel_two_ranks_on_one_gpu(nb):
     def scratch():
         return torch.zeros(int(dll.nerf_adam_fused_scratch_bytes(n)) // 8, device=DEV, dtype=torch.float64)
 
-    for world in (1, 2):
+    for world, two_shot in ((1, False), (2, False), (1, True), (2, True), (3, True)):
         p_init = torch.randn(n, generator=g, **f32)
-        bufs = [torch.zeros(n_pad + n_flags, **f32) for _ in range(world)]
+        bufs = [torch.zeros(2 * n_pad + n_flags, **f32) for _ in range(world)]     # gradient | reduced gradient | flags
         arr = ctypes.c_void_p * world
         grads_arr = arr(*[b.data_ptr() for b in bufs])
-        flags_arr = arr(*[b.data_ptr() + 4 * n_pad for b in bufs])
+        red_arr = arr(*[b.data_ptr() + 4 * n_pad for b in bufs]) if two_shot else None
+        flags_arr = arr(*[b.data_ptr() + 8 * n_pad for b in bufs])
         ranks = [dict(p=p_init.clone(), m=torch.zeros(n, **f32), v=torch.zeros(n, **f32), st=state(world), sc=scratch(),
                       stream=torch.cuda.Stream()) for _ in range(world)]
         ref = dict(p=p_init.clone(), m=torch.zeros(n, **f32), v=torch.zeros(n, **f32), st=state(world), sc=scratch())
@@ -326,7 +329,7 @@ def test_peer_gradient_exchange_kernel_two_ranks_on_one_gpu(nb):
             torch.cuda.synchronize()
             for r, rk in enumerate(ranks):
                 with torch.cuda.stream(rk["stream"]):
-                    _lib.check(dll.nerf_adam_step_fused_peer(ptr(rk["p"]), grads_arr, flags_arr, r, world, ptr(rk["m"]), ptr(rk["v"]),
+                    _lib.check(dll.nerf_adam_step_fused_peer(ptr(rk["p"]), grads_arr, red_arr, flags_arr, r, world, ptr(rk["m"]), ptr(rk["v"]),
                                                              n, ptr(rk["st"]), ptr(loss), ptr(rk["sc"]),
                                                              ctypes.c_void_p(rk["stream"].cuda_stream)), "peer")
             _lib.check(dll.nerf_adam_step_fused(ptr(ref["p"]), ptr(total), ptr(ref["m"]), ptr(ref["v"]), n, ptr(ref["st"]),
@@ -334,11 +337,11 @@ def test_peer_gradient_exchange_kernel_two_ranks_on_one_gpu(nb):
             torch.cuda.synchronize()
             for rk in ranks:
                 for k in ("p", "m", "v"):
-                    assert torch.equal(rk[k], ref[k]), (world, step, k)
-                assert torch.equal(rk["st"][:12], ref["st"][:12]), (world, step)     # scalars, step counter, loss, psnr
+                    assert torch.equal(rk[k], ref[k]), (world, two_shot, step, k)
+                assert torch.equal(rk["st"][:12], ref["st"][:12]), (world, two_shot, step)     # scalars, step counter, loss, psnr
                 # grad norm: fp64 sum of squares, partial sums grouped per float4 here and per element there
                 assert abs(float(rk["st"][12]) - float(ref["st"][12])) <= 1e-12 * float(ref["st"][12])
             for b, lg in zip(bufs, local):
                 assert torch.equal(b[:n], lg)                     # the gradient buffers keep the rank-local gradients
-                flags = b[n_pad:].view(torch.int32)
+                flags = b[2 * n_pad:].view(torch.int32)
                 assert int(flags[2 * _lib.PEER_MAX]) == step + 1  # epoch
