@@ -123,12 +123,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.proc, self.lines, self.skip = gpu_index, None, [], 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -138,6 +138,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def mark(self):
+        """Samples delivered so far are from before the region of interest (the sampler is started early because
+        nvidia-smi needs a few hundred ms to deliver its first line)."""
+        self.skip = len(self.lines)
+        return self
 
     def stop(self):
         if self.proc is None:
@@ -150,7 +156,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.skip:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -427,6 +433,7 @@ def bench_train(cx, args, rays, K, W, full=True):
     import torch.distributed as td
     nb, ops, dev, world, rank = cx.nb, cx.ops, cx.dev, cx.world, cx.rank
     dll = nb._lib.dll()
+    sampler = ClockSampler(cx.local).start()                    # started early: see ClockSampler.mark
     torch.manual_seed(0)
     model = nb.NeRFMLP(precision=args.precision).to(dev)       # random-init 8x256 (torch default init)
     if world > 1:
@@ -477,7 +484,7 @@ def bench_train(cx, args, rays, K, W, full=True):
     # --- warm-up, then EXACTLY K timed steps (device time, per-step events, L2 flushed in between) ---
     # (the clock sampler starts before the warm-up: nvidia-smi needs a few hundred ms to deliver its first sample and a
     #  20-step timed region lasts ~20 ms; the warm-up steps run the same kernels at the same clocks)
-    sampler = ClockSampler(cx.local).start()
+    sampler.mark()
     for _ in range(W):
         run()
     cx.barrier()
@@ -530,7 +537,7 @@ def bench_train(cx, args, rays, K, W, full=True):
     # data-parallel step is collective)
     extra = 0
     for _ in range(40):
-        got = torch.tensor([1.0 if (sampler.lines or sampler.proc is None) else 0.0], device=dev)
+        got = torch.tensor([1.0 if (len(sampler.lines) > sampler.skip or sampler.proc is None) else 0.0], device=dev)
         if world > 1:
             td.all_reduce(got, op=td.ReduceOp.MIN)
         if float(got) > 0:
