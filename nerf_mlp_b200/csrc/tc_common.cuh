@@ -72,6 +72,7 @@ constexpr int kMaxSlots = 192;
 //           mask  u32  [8][M][8]     ReLU masks of h0..h7; hvmask u32 [M][4]   (row-major, save only)
 // backward: dpre  img  [9][Mp x 256] d(pre-activation) of layers 0..7, d(bottleneck); dhv img [Mp x 128]
 //           flags u32  [10][Mp/128]   fused backward: number of warps that have published (d_pre_0..7, d_bott, d_hv) of a tile
+//                      + 32 words (unit counter) + 128 words (wgrad roles' progress, read by the unit throttle)
 //           -- Mp = rows padded to a multiple of 512 (whole tile quads per CTA pair)
 struct WsLayout {
   size_t vb, de, act, hv, xenc, de16, mask, hvmask, dpre, dhv, flags, total;
