@@ -85,3 +85,22 @@ def allreduce_flat(flat, group=None):
     if world > 1:
         td.all_reduce(flat, op=td.ReduceOp.SUM, group=group)
     return world
+
+
+def peer_exchange_layout(n_params: int, world: int, two_shot=None, peer_max: int = 8):
+    """Layout of one rank's symmetric block for TrainStep's peer-memory gradient exchange
+    (nerf_adam_step_fused_peer): ``{"two_shot", "n_pad", "grad_off", "red_off", "flag_off", "floats"}`` in floats.
+    One-shot (every rank reads all gradients) below 4 ranks, two-shot (reduce-scatter + all-gather through a second
+    n-float region) from 4 ranks up; ``two_shot`` (or the environment variable NERF_PEER_TWO_SHOT=0|1) overrides."""
+    import os
+    if not 1 <= world <= peer_max:
+        raise ValueError(f"peer-memory gradient exchange supports 1..{peer_max} ranks, got {world}")
+    if two_shot is None:
+        env = os.environ.get("NERF_PEER_TWO_SHOT", "")
+        two_shot = (world >= 4) if env == "" else (env != "0")
+    n_pad = (int(n_params) + 127) // 128 * 128                    # 512-byte granules: every region stays 16-byte aligned
+    n_data = (2 if two_shot else 1) * n_pad
+    n_flags = 2 * peer_max + 32                                   # ready flags | slice / read-done flags | epoch, counter
+    return {"two_shot": bool(two_shot), "n_pad": n_pad, "grad_off": 0, "red_off": n_pad if two_shot else None,
+            "flag_off": n_data, "floats": n_data + n_flags}
+

@@ -23,11 +23,11 @@ Data-parallel (world_size > 1): the step is two graphs with ONE flat NCCL all-re
 from __future__ import annotations
 
 import math
-import os
 
 import torch
 
 from . import _lib, ops
+from . import dist as dist_mod
 from ._lib import check, dll, ptr, stream_ptr
 
 _ST_LR, _ST_B1, _ST_B2, _ST_EPS, _ST_SCALE, _ST_STEP = range(6)
@@ -221,12 +221,9 @@ class TrainStep:
                 raise RuntimeError("no initialised process group" if world <= _lib.PEER_MAX else f"world {world} > {_lib.PEER_MAX}")
             group = self.opt.process_group if self.opt.process_group is not None else dist.group.WORLD
             n = m.flat_params.numel()
-            n_pad = (n + 127) // 128 * 128
-            n_flags = 2 * _lib.PEER_MAX + 32
-            # two-shot exchange (reduce-scatter + all-gather) from 4 ranks up: a second n-float region for the reduced gradient
-            env = os.environ.get("NERF_PEER_TWO_SHOT", "")
-            two_shot = (world >= 4) if env == "" else (env != "0")
-            buf = symm.empty((2 if two_shot else 1) * n_pad + n_flags, dtype=torch.float32, device=self.dev)
+            lay = dist_mod.peer_exchange_layout(n, world, peer_max=_lib.PEER_MAX)
+            two_shot = lay["two_shot"]
+            buf = symm.empty(lay["floats"], dtype=torch.float32, device=self.dev)
             buf.zero_()
             hdl = symm.rendezvous(buf, group)
             ptrs = [int(x) for x in hdl.buffer_ptrs]
@@ -235,10 +232,9 @@ class TrainStep:
             torch.cuda.synchronize(self.dev)
             dist.barrier(group)                                   # every rank's flags are zero before anybody's first step
             arr = ctypes.c_void_p * world
-            n_data = (2 if two_shot else 1) * n_pad
             self._peer = {"buf": buf, "hdl": hdl, "rank": int(hdl.rank), "world": world, "n": n, "two_shot": two_shot,
-                          "grads": arr(*ptrs), "red": arr(*[q + 4 * n_pad for q in ptrs]) if two_shot else None,
-                          "flags": arr(*[q + 4 * n_data for q in ptrs])}
+                          "grads": arr(*ptrs), "red": arr(*[q + 4 * lay["red_off"] for q in ptrs]) if two_shot else None,
+                          "flags": arr(*[q + 4 * lay["flag_off"] for q in ptrs])}
             for prm in m._param_list:                             # re-bind the parameters' .grad views to the new buffer
                 prm.grad = None
             m._flat_grad = buf[:n]

@@ -334,3 +334,26 @@ def test_oracle_is_only_reachable_from_checker_and_baseline_code():
         if isinstance(node, ast.FunctionDef):
             uses = [n for n in ast.walk(node) if isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle")]
             assert not uses or node.name in allowed, node.name
+
+
+def test_peer_exchange_layout(monkeypatch):
+    """Host side of TrainStep's peer-memory gradient exchange: one-shot below 4 ranks, two-shot from 4 up (second
+    n-float region), every region 16-byte aligned, the flag block behind the data, the environment override."""
+    from nerf_mlp_b200 import _lib
+    from nerf_mlp_b200.dist import peer_exchange_layout
+    monkeypatch.delenv("NERF_PEER_TWO_SHOT", raising=False)
+    n = 595_844                                                    # the reference network's parameter count
+    for world in range(1, 9):
+        lay = peer_exchange_layout(n, world, peer_max=_lib.PEER_MAX)
+        assert lay["two_shot"] == (world >= 4)
+        assert lay["n_pad"] >= n and lay["n_pad"] % 128 == 0 and lay["grad_off"] == 0
+        assert lay["red_off"] == (lay["n_pad"] if world >= 4 else None)
+        assert lay["flag_off"] == (2 if world >= 4 else 1) * lay["n_pad"]
+        assert lay["floats"] - lay["flag_off"] >= 2 * _lib.PEER_MAX + 2      # ready | slice flags, epoch, block counter
+    monkeypatch.setenv("NERF_PEER_TWO_SHOT", "1")
+    assert peer_exchange_layout(n, 2)["two_shot"] is True
+    monkeypatch.setenv("NERF_PEER_TWO_SHOT", "0")
+    assert peer_exchange_layout(n, 8)["two_shot"] is False
+    assert peer_exchange_layout(n, 8, two_shot=True)["two_shot"] is True     # the explicit argument wins
+    with pytest.raises(ValueError):
+        peer_exchange_layout(n, 9)
