@@ -294,7 +294,7 @@ __device__ __forceinline__ void st_peer_v4(float* p, float4 v) {
 }
 __device__ __forceinline__ void st_peer(float* p, float v) { asm volatile("st.volatile.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
-__global__ void __launch_bounds__(256) adam_fused_peer2_kernel(float* __restrict__ p, const PeerArgs pa, float* __restrict__ m,
+__global__ void __launch_bounds__(256, 4) adam_fused_peer2_kernel(float* __restrict__ p, const PeerArgs pa, float* __restrict__ m,
                                                                float* __restrict__ v, int64_t n, double* __restrict__ st,
                                                                const float* __restrict__ loss, double* __restrict__ scratch) {
   __shared__ float sc[7];
@@ -436,12 +436,24 @@ extern "C" int nerf_adam_step_fused_peer(float* params, const float* const* peer
   }
   const int64_t n4 = n >> 2;
   int blocks = (int)(ceil_div(n4 > 0 ? n4 : 1, 256) < 592 ? ceil_div(n4 > 0 ? n4 : 1, 256) : 592);
-  // both kernels spin on flags written by other blocks / ranks: the whole grid must be co-resident (592 blocks of 256
-  // threads are at most 4 per SM on 148 SMs; smaller devices get a smaller grid)
+  // The two-shot kernel's blocks wait (for the peers' slices) while other blocks of the same grid still have to run
+  // their scatter phase: its whole grid must be co-resident, so the grid is capped at what the occupancy calculator
+  // says fits (the kernel is bounded to 64 registers: 4 blocks per SM).  The one-shot kernel's blocks never wait for
+  // another block of their own grid, but the same cap costs nothing (both kernels are grid-stride loops).
   DeviceProps dp;
   int rc = current_device(&dp);
   if (rc) return rc;
-  if (blocks > 4 * dp.sm_count) blocks = 4 * dp.sm_count;
+  static int occ[2][kMaxDevices];
+  static DeviceOnce occ_done;
+  if (occ_done.needed(dp.ordinal)) {
+    int o1 = 0, o2 = 0;
+    NERF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, adam_fused_peer_kernel, 256, 0));
+    NERF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, adam_fused_peer2_kernel, 256, 0));
+    if (dp.ordinal >= 0 && dp.ordinal < kMaxDevices) { occ[0][dp.ordinal] = o1 < 1 ? 1 : o1; occ[1][dp.ordinal] = o2 < 1 ? 1 : o2; }
+    occ_done.mark(dp.ordinal);
+  }
+  const int per_sm = (dp.ordinal >= 0 && dp.ordinal < kMaxDevices) ? occ[peer_red != nullptr ? 1 : 0][dp.ordinal] : 1;
+  if (blocks > per_sm * dp.sm_count) blocks = per_sm * dp.sm_count;
   if (peer_red != nullptr)
     adam_fused_peer2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, pa, exp_avg, exp_avg_sq, n, state, loss, (double*)scratch);
   else
